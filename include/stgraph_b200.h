@@ -1,0 +1,201 @@
+/*
+ * stgraph_b200 -- C ABI of the B200-native backend for STGraph's vertex-centric
+ * aggregation hot path.
+ *
+ * Every entry point:
+ *   - takes plain device (or, where the name ends in _host, host) pointers and sizes,
+ *   - takes an explicit cudaStream_t (as void*) and enqueues work on it: no
+ *     synchronisation, no allocation behind the caller's back (workspaces are
+ *     passed in; sizes are queried with the *_workspace_bytes functions), so all
+ *     device-pointer entry points are CUDA-graph capturable,
+ *   - returns 0 on success or a negative StgStatus; it never throws and never
+ *     prints.  stg_last_error() returns a thread-local description.
+ *
+ * "Replaces" comments cite the reference interface each entry point stands in
+ * for (paths relative to the STGraph source tree, v1.1.0).
+ */
+#ifndef STGRAPH_B200_H_
+#define STGRAPH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STG_ABI_VERSION 1
+
+typedef enum StgStatus {
+  STG_OK = 0,
+  STG_ERR_INVALID_ARGUMENT = -1,
+  STG_ERR_CUDA = -2,
+  STG_ERR_UNSUPPORTED = -3,
+  STG_ERR_WORKSPACE_TOO_SMALL = -4,
+  STG_ERR_CAPACITY = -5
+} StgStatus;
+
+/* One direction of a graph snapshot in CSR form -- the same four device arrays
+ * the reference hands to every generated kernel
+ * (stgraph/graph/stgraph_base.py:51-59; kernel signature
+ * stgraph/compiler/code_gen/templates/fa/tpl_fa_csr.jinja:1-11).
+ * Rows are destinations for the forward (in-edge) view and sources for the
+ * backward (out-edge) view. */
+typedef struct StgCsrView {
+  const int32_t* row_offset;     /* [num_nodes+1] */
+  const int32_t* column_indices; /* [num_edges]   */
+  const int32_t* eids;           /* [num_edges] edge id (or 1-based label) of each slot; may be NULL when eids_identity */
+  const int32_t* node_ids;       /* [num_nodes] degree-descending row order; may be NULL (natural order) */
+  int32_t num_nodes;
+  int32_t num_edges;
+  int32_t eid_base;      /* 0 for CSR (StaticGraph/NaiveGraph), 1 for PCSR/GPMA labels
+                            (tpl_fa_pcsr.jinja:32-34, tpl_fa_gpma.jinja:32-34) */
+  int32_t eids_identity; /* 1 if eids[i] == i + eid_base for all i (forward StaticGraph) */
+  /* Optional hub-row schedule (rows longer than hub_threshold are processed by a
+   * block-per-row kernel).  hub_rows/hub_count are device arrays produced by
+   * stg_csr_hub_rows(); NULL disables the split. */
+  const int32_t* hub_rows;
+  const int32_t* hub_count;
+  int32_t hub_threshold;
+  int32_t hub_capacity;
+} StgCsrView;
+
+/* ------------------------------------------------------------------ misc */
+int stg_abi_version(void);
+const char* stg_last_error(void);
+/* Device properties the Python side sizes grids/benchmarks with. */
+int stg_device_info(int device, int32_t* sm_count, int64_t* l2_bytes, int32_t* cc_major, int32_t* cc_minor);
+
+/* ----------------------------------------------------- aggregation (hot) */
+/* out[r,:] = row_scale[r] * sum_{e in row r} nbr_scale[col[e]] * edge_scale[eid(e)] * x[col[e],:]
+ *
+ * Replaces the generated Seastar kernels K0/K1 for GCNConv
+ * (stgraph/nn/pytorch/static/gcn_conv.py:162-182; emitted from
+ * templates/fa/tpl_fa_csr*.jinja:1-57 and launched by
+ * stgraph/compiler/execution_unit.py:359-372).  With the in-edge view it is the
+ * forward aggregation, with the out-edge view and x = grad_out the backward one.
+ * Any of nbr_scale [N], edge_scale [E], row_scale [N] may be NULL (= 1).
+ * x and out are row-major fp32 [num_nodes, feat]; they must not alias. */
+int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t feat,
+                           const float* nbr_scale, const float* edge_scale,
+                           const float* row_scale, float* out, void* stream);
+
+/* Same operation with HOST buffers: copies x (and the scale vectors) to the
+ * device scratch the caller provides, runs the kernel, copies out back.
+ * dev_scratch must hold 2*N*feat + 2*N + E floats.  Used for the end-to-end
+ * (host-to-host) figure in bench.py; synchronises the stream before returning. */
+int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host, int32_t feat,
+                                const float* nbr_scale_host, const float* edge_scale_host,
+                                const float* row_scale_host, float* out_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* Fused edge-softmax attention aggregation (one pass, online softmax per head):
+ *   score_e = leaky_relu(el[col[e],h] + er[r,h]);  alpha = softmax over the row
+ *   out[r,h,:] = sum_e alpha_e * feat[col[e],h,:]
+ * row_max / row_sum ([N,H]) are saved for the backward pass.
+ * Replaces the two-kernel K0+K1 sequence of GATConv with a materialised [E,H]
+ * tensor (stgraph/nn/pytorch/static/gat_conv.py:48-56). */
+int stg_gat_softmax_fwd_f32(const StgCsrView* g_in, const float* el, const float* er,
+                            const float* feat, int32_t heads, int32_t dim, float slope,
+                            float* out, float* row_max, float* row_sum, void* stream);
+/* Backward of the above, atomic-free: a destination-parallel pass over the
+ * in-edge view produces d_er and the per-destination dot products, a
+ * source-parallel pass over the out-edge view produces d_feat and d_el.
+ * dot_scratch: [N,H] floats.  Replaces K2 and its E*H*D atomics. */
+int stg_gat_softmax_bwd_f32(const StgCsrView* g_in, const StgCsrView* g_out,
+                            const float* el, const float* er, const float* feat,
+                            const float* out, const float* grad_out,
+                            const float* row_max, const float* row_sum,
+                            int32_t heads, int32_t dim, float slope,
+                            float* d_feat, float* d_el, float* d_er,
+                            float* dot_scratch, void* stream);
+
+/* ------------------------------------------- generic fused vertex program */
+/* A lowered execution unit: straight-line register code evaluated per
+ * (row, feature lane) with one pass over the row's edges.  Replaces the Jinja
+ * code generator + run-time nvcc (stgraph/compiler/code_gen/code_gen.py:39-116,
+ * compiler.py:14-44): the traced IR is interpreted by one pre-compiled kernel. */
+enum { STG_VM_MAX_TENSORS = 24, STG_VM_MAX_INSTR = 96, STG_VM_MAX_REGS = 48, STG_VM_MAX_ACC = 8 };
+
+typedef enum StgVmSide { STG_VM_CENTER = 0, STG_VM_NBR = 1, STG_VM_EDGE = 2, STG_VM_PARAM = 3 } StgVmSide;
+typedef enum StgVmPhase { STG_VM_PRE = 0, STG_VM_LOOP = 1, STG_VM_POST = 2 } StgVmPhase;
+typedef enum StgVmOp {
+  STG_OP_LOAD = 0,   /* r[dst] = tensor[a] (indexed by its side, broadcast by size) */
+  STG_OP_CONST,      /* r[dst] = imm */
+  STG_OP_ADD, STG_OP_SUB, STG_OP_MUL, STG_OP_DIV,   /* r[dst] = r[a] op r[b] */
+  STG_OP_EXP,        /* r[dst] = expf(r[a]) */
+  STG_OP_LRELU,      /* r[dst] = r[a] > 0 ? r[a] : imm * r[a] */
+  STG_OP_LRELU_BWD,  /* r[dst] = r[a] > 0 ? 1 : imm */
+  STG_OP_RELU,       /* r[dst] = r[a] > 0 ? r[a] : 0 */
+  STG_OP_RELU_BWD,   /* r[dst] = r[a] > 0 ? r[b] : 0 */
+  STG_OP_AMAX_BWD,   /* r[dst] = r[a] == r[b] ? 1 : 0 */
+  STG_OP_ACC_SUM,    /* acc[dst] += r[a]             (LOOP only) */
+  STG_OP_ACC_MAX,    /* acc[dst] = max(acc[dst], r[a]) */
+  STG_OP_ACC_MIN,
+  STG_OP_ACC_READ,   /* r[dst] = acc[a]; b=1: divide by the row length (AggMean) (POST only) */
+  STG_OP_STORE,      /* tensor[a] = r[b]; imm!=0: sum over the tensor's broadcast group first */
+  STG_OP_COUNT_
+} StgVmOp;
+
+typedef struct StgVmTensor {
+  int32_t side;  /* StgVmSide */
+  int32_t size;  /* elements per node/edge (1 for params of size 1); must divide lanes */
+} StgVmTensor;
+
+typedef struct StgVmInstr {
+  int16_t op;    /* StgVmOp */
+  int16_t phase; /* StgVmPhase */
+  int16_t dst, a, b;
+  int16_t pad;
+  float imm;
+} StgVmInstr;
+
+typedef struct StgVmProgram {
+  int32_t lanes;       /* feature lanes per row = product of the unit's max dims */
+  int32_t n_tensors, n_instr, n_regs, n_acc;
+  float acc_init[STG_VM_MAX_ACC];
+  StgVmTensor tensors[STG_VM_MAX_TENSORS];
+  StgVmInstr instr[STG_VM_MAX_INSTR];
+} StgVmProgram;
+
+int stg_vm_run_f32(const StgCsrView* g, const StgVmProgram* prog, void* const* tensors, void* stream);
+
+/* --------------------------------------------------- graph structure ops */
+/* Workspace needed by stg_csr_build for E edges / N nodes. */
+size_t stg_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes);
+
+/* Builds both directions of a static graph on the GPU from an (unsorted) edge list.
+ *   forward : rows = dst, sorted by (dst,src); fwd_eids[i] = i
+ *   backward: rows = src, sorted by (src,dst); bwd_eids = forward eid of each edge
+ *   in_degree / out_degree [N]; fwd/bwd node_ids [N] = rows by non-increasing length
+ *   (stable, ascending id within a tie).
+ * edge_perm [E] (optional): edge_perm[i] = position in the caller's list of the
+ * edge that received forward eid i (lets callers permute their edge weights).
+ * num_unique (optional, device int32): number of distinct (src,dst) pairs
+ * (static_graph.py:49 sizes edge tensors by len(set(edge_list))).
+ * Replaces the host loop + 4 cudaMemcpy of CSR::CSR
+ * (stgraph/graph/static/csr.cu:68-170) and the Python tuple sorts of
+ * stgraph/graph/static/static_graph.py:65-78. */
+int stg_csr_build(const int32_t* src, const int32_t* dst, int64_t num_edges, int32_t num_nodes,
+                  int32_t* fwd_row_offset, int32_t* fwd_col, int32_t* fwd_eids, int32_t* fwd_node_ids,
+                  int32_t* bwd_row_offset, int32_t* bwd_col, int32_t* bwd_eids, int32_t* bwd_node_ids,
+                  int32_t* in_degree, int32_t* out_degree, int32_t* edge_perm, int32_t* num_unique,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* norm[v] = deg[v] > 0 ? deg[v]^-0.5 : 0   (benchmarking/gcn/seastar/train.py:53-57) */
+int stg_degree_norm_f32(const int32_t* degree, int32_t num_nodes, float* norm, void* stream);
+
+/* weighted_degree[r] = sum over row r of w[eid]  (csr.cu:126, fp32, row order) */
+int stg_weighted_row_degree_f32(const StgCsrView* g, const float* edge_weight, float* out, void* stream);
+
+/* hub_rows = { r : row length > threshold }, *hub_count = how many (clamped to capacity). */
+int stg_csr_hub_rows(const int32_t* row_offset, int32_t num_nodes, int32_t threshold,
+                     int32_t* hub_rows, int32_t capacity, int32_t* hub_count, void* stream);
+
+/* D2H copy of an int32 device array -- test hook (csr.cu:172-179 get_array). */
+int stg_get_array_i32(const int32_t* dev_ptr, int64_t count, int32_t* host_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STGRAPH_B200_H_ */

@@ -1,0 +1,348 @@
+// Fused neighbour aggregation (gather - scale - sum) for sm_100a.
+//
+//   out[r,:] = row_scale[r] * sum_{e in row r} nbr_scale[col[e]] * edge_scale[eid(e)] * x[col[e],:]
+//
+// This is the one kernel shape on STGraph's hot path: the reference emits it
+// from stgraph/compiler/code_gen/templates/fa/tpl_fa_csr*.jinja:1-57 with one
+// thread per (row, feature) and a serial edge loop of scalar loads.  Here:
+//   * a GROUP of lanes (1..32, power of two) owns a row and each lane owns VEC
+//     (1/2/4) consecutive floats x NACC chunks, so one neighbour row is fetched
+//     with 128-bit coalesced loads;
+//   * column indices / scales of the next GROUP edges are loaded cooperatively
+//     (one coalesced load per group) and prefetched one batch ahead, then
+//     broadcast with warp shuffles;
+//   * UNROLL independent neighbour-row loads are in flight per lane;
+//   * rows longer than hub_threshold go to a block-per-row kernel whose warps
+//     split the row and reduce through shared memory in a fixed order
+//     (deterministic: no atomics anywhere).
+// Memory bound: HBM roofline; algorithmic bytes per launch
+//   4*(2*N*F + E + (N+1) + 2*N [+ E for edge_scale]).
+#include "common.cuh"
+
+namespace stg {
+namespace {
+
+constexpr int kBlockThreads = 256;
+constexpr int kHubThreads = 512;
+
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type ld_row(const float* p) {
+  using T = typename VecT<VEC>::type;
+  return __ldg(reinterpret_cast<const T*>(p));
+}
+template <int VEC>
+__device__ __forceinline__ void st_row(float* p, typename VecT<VEC>::type v) {
+  using T = typename VecT<VEC>::type;
+  __stcs(reinterpret_cast<T*>(p), v);
+}
+
+struct AggParams {
+  const int32_t* __restrict__ row_off;
+  const int32_t* __restrict__ col;
+  const int32_t* __restrict__ eids;
+  const int32_t* __restrict__ hub_rows;
+  const int32_t* __restrict__ hub_count;
+  int num_rows;
+  int eid_base;
+  int eids_identity;
+  int hub_threshold;
+  int hub_capacity;
+  const float* __restrict__ x;    // already offset to the chunk's first column
+  float* __restrict__ out;        // same
+  int ld;                         // floats between consecutive rows (= feat)
+  int width;                      // floats of this chunk handled by the launch
+  const float* __restrict__ ns;
+  const float* __restrict__ es;
+  const float* __restrict__ rs;
+};
+
+// Accumulate edges [beg,end) visited with stride `step` batches of GROUP edges,
+// starting at batch `first`.  All lanes of a group execute this together.
+template <int VEC, int GROUP, int NACC>
+__device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
+                                                 int batch_step, int gl, unsigned gmask,
+                                                 typename VecT<VEC>::type (&acc)[NACC]) {
+  using T = typename VecT<VEC>::type;
+  constexpr int UNROLL = (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
+  bool act[NACC];
+  int off[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    off[k] = (gl + k * GROUP) * VEC;
+    act[k] = off[k] < p.width;
+  }
+
+  auto load_meta = [&](int base, int& c, float& s) {
+    c = 0;
+    s = 0.f;
+    const int e = base + gl;
+    if (e < end) {
+      c = ld_stream(p.col + e);
+      float sc = 1.f;
+      if (p.ns) sc = __ldg(p.ns + c);
+      if (p.es) {
+        const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
+        sc *= __ldg(p.es + eid);
+      }
+      s = sc;
+    }
+  };
+
+  int base = beg + first_batch * GROUP;
+  int my_c, nx_c;
+  float my_s, nx_s;
+  load_meta(base, my_c, my_s);
+  for (; base < end; base += batch_step * GROUP) {
+    load_meta(base + batch_step * GROUP, nx_c, nx_s);   // prefetch next batch
+    const int n = min(GROUP, end - base);
+    for (int j = 0; j < n; j += UNROLL) {
+      int c[UNROLL];
+      float s[UNROLL];
+      T v[UNROLL][NACC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        c[u] = __shfl_sync(gmask, my_c, j + u, GROUP);
+        s[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const float* src = p.x + static_cast<size_t>(c[u]) * p.ld;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          if (act[k] && (j + u) < n) v[u][k] = ld_row<VEC>(src + off[k]);
+          else zero_vec(v[u][k]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], s[u], v[u][k]);
+      }
+    }
+    my_c = nx_c;
+    my_s = nx_s;
+  }
+}
+
+template <int VEC, int GROUP, int NACC>
+__global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
+  using T = typename VecT<VEC>::type;
+  constexpr int GROUPS_PER_WARP = 32 / GROUP;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (GROUP - 1);
+  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
+  const int warp = blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5);
+  const int row = warp * GROUPS_PER_WARP + lane / GROUP;
+  if (row >= p.num_rows) return;
+  const int beg = __ldg(p.row_off + row);
+  const int end = __ldg(p.row_off + row + 1);
+  if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) return;  // hub kernel owns this row
+
+  T acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+  accumulate_edges<VEC, GROUP, NACC>(p, beg, end, 0, 1, gl, gmask, acc);
+
+  const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+  float* dst = p.out + static_cast<size_t>(row) * p.ld;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    const int o = (gl + k * GROUP) * VEC;
+    if (o < p.width) {
+      scale_vec(acc[k], r);
+      st_row<VEC>(dst + o, acc[k]);
+    }
+  }
+}
+
+// Block per hub row: every (warp, group) pair takes a strided share of the row's
+// edge batches; partials are reduced group->warp by shuffles and warp->block
+// through shared memory in a fixed order.
+template <int VEC, int GROUP, int NACC>
+__global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p) {
+  using T = typename VecT<VEC>::type;
+  constexpr int GROUPS_PER_WARP = 32 / GROUP;
+  constexpr int WARPS = kHubThreads / 32;
+  __shared__ T partial[WARPS][GROUP * NACC];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int gl = lane & (GROUP - 1);
+  const int gidx = lane / GROUP;
+  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
+  const int n_hub = min(__ldg(p.hub_count), p.hub_capacity);
+  for (int i = blockIdx.x; i < n_hub; i += gridDim.x) {
+    const int row = __ldg(p.hub_rows + i);
+    const int beg = __ldg(p.row_off + row);
+    const int end = __ldg(p.row_off + row + 1);
+    T acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+    accumulate_edges<VEC, GROUP, NACC>(p, beg, end, wid * GROUPS_PER_WARP + gidx,
+                                       WARPS * GROUPS_PER_WARP, gl, gmask, acc);
+    // groups of one warp -> lanes [0, GROUP)
+#pragma unroll
+    for (int o = GROUP; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        T other;
+        if constexpr (VEC == 1) {
+          other = __shfl_xor_sync(0xffffffffu, acc[k], o);
+        } else if constexpr (VEC == 2) {
+          other.x = __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+          other.y = __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+        } else {
+          other.x = __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+          other.y = __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+          other.z = __shfl_xor_sync(0xffffffffu, acc[k].z, o);
+          other.w = __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+        }
+        add_vec(acc[k], other);
+      }
+    }
+    if (lane < GROUP) {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) partial[wid][k * GROUP + lane] = acc[k];
+    }
+    __syncthreads();
+    if (wid == 0 && lane < GROUP) {
+      const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+      float* dst = p.out + static_cast<size_t>(row) * p.ld;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        T sum = partial[0][k * GROUP + lane];
+        for (int w = 1; w < WARPS; ++w) add_vec(sum, partial[w][k * GROUP + lane]);
+        const int o = (lane + k * GROUP) * VEC;
+        if (o < p.width) {
+          scale_vec(sum, r);
+          st_row<VEC>(dst + o, sum);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC, int GROUP, int NACC>
+int launch_agg(const AggParams& p, cudaStream_t stream) {
+  constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
+  const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
+  if (blocks > 0) {
+    agg_rows_kernel<VEC, GROUP, NACC><<<blocks, kBlockThreads, 0, stream>>>(p);
+    STG_LAUNCH_CHECK("agg_rows_kernel");
+  }
+  if (p.hub_threshold > 0 && p.hub_rows != nullptr) {
+    agg_hub_kernel<VEC, GROUP, NACC><<<2 * sm_count(), kHubThreads, 0, stream>>>(p);
+    STG_LAUNCH_CHECK("agg_hub_kernel");
+  }
+  return STG_OK;
+}
+
+template <int VEC>
+int dispatch_group(const AggParams& p, cudaStream_t stream) {
+  const int nvec = p.width / VEC;
+  if (nvec <= 1) return launch_agg<VEC, 1, 1>(p, stream);
+  if (nvec <= 2) return launch_agg<VEC, 2, 1>(p, stream);
+  if (nvec <= 4) return launch_agg<VEC, 4, 1>(p, stream);
+  if (nvec <= 8) return launch_agg<VEC, 8, 1>(p, stream);
+  if (nvec <= 16) return launch_agg<VEC, 16, 1>(p, stream);
+  if (nvec <= 32) return launch_agg<VEC, 32, 1>(p, stream);
+  if (nvec <= 64) return launch_agg<VEC, 32, 2>(p, stream);
+  return launch_agg<VEC, 32, 4>(p, stream);
+}
+
+}  // namespace
+
+int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, const float* ns,
+                          const float* es, const float* rs, float* out, cudaStream_t stream) {
+  AggParams p;
+  p.row_off = g->row_offset;
+  p.col = g->column_indices;
+  p.eids = g->eids;
+  p.hub_rows = g->hub_rows;
+  p.hub_count = g->hub_count;
+  p.num_rows = g->num_nodes;
+  p.eid_base = g->eid_base;
+  p.eids_identity = g->eids_identity;
+  p.hub_threshold = (g->hub_rows && g->hub_count) ? g->hub_threshold : 0;
+  p.hub_capacity = g->hub_capacity;
+  p.ld = feat;
+  p.ns = ns;
+  p.es = es;
+  p.rs = rs;
+  int vec = 1;
+  if (feat % 4 == 0 && aligned16(x) && aligned16(out)) vec = 4;
+  else if (feat % 2 == 0 && aligned8(x) && aligned8(out)) vec = 2;
+  const int chunk = 32 * 4 * vec;  // widest tile one launch covers
+  for (int f0 = 0; f0 < feat; f0 += chunk) {
+    p.x = x + f0;
+    p.out = out + f0;
+    p.width = min(chunk, feat - f0);
+    int rc;
+    if (vec == 4) rc = dispatch_group<4>(p, stream);
+    else if (vec == 2) rc = dispatch_group<2>(p, stream);
+    else rc = dispatch_group<1>(p, stream);
+    if (rc != STG_OK) return rc;
+  }
+  return STG_OK;
+}
+
+}  // namespace stg
+
+using namespace stg;
+
+static int validate_view(const StgCsrView* g, bool need_eids) {
+  STG_CHECK_ARG(g != nullptr, "graph view is NULL");
+  STG_CHECK_ARG(g->num_nodes >= 0 && g->num_edges >= 0, "negative graph size (%d nodes, %d edges)",
+                g->num_nodes, g->num_edges);
+  STG_CHECK_ARG(g->row_offset != nullptr, "row_offset is NULL");
+  STG_CHECK_ARG(g->num_edges == 0 || g->column_indices != nullptr, "column_indices is NULL");
+  STG_CHECK_ARG(!need_eids || g->eids_identity || g->num_edges == 0 || g->eids != nullptr,
+                "eids is NULL but an edge tensor is indexed by edge id");
+  return STG_OK;
+}
+
+STG_API int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t feat,
+                                      const float* nbr_scale, const float* edge_scale,
+                                      const float* row_scale, float* out, void* stream) {
+  int rc = validate_view(g, edge_scale != nullptr);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
+  STG_CHECK_ARG(x != out, "x and out must not alias");
+  return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream));
+}
+
+STG_API int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host, int32_t feat,
+                                           const float* nbr_scale_host, const float* edge_scale_host,
+                                           const float* row_scale_host, float* out_host,
+                                           void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  int rc = validate_view(g, edge_scale_host != nullptr);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(x_host && out_host && dev_scratch, "host buffers / scratch must not be NULL");
+  const size_t n = static_cast<size_t>(g->num_nodes), e = static_cast<size_t>(g->num_edges);
+  const size_t nf = align_up(n * feat, 4), n4 = align_up(n, 4), e4 = align_up(e, 4);
+  const size_t need = (2 * nf + 2 * n4 + e4) * sizeof(float);
+  if (dev_scratch_bytes < need) {
+    set_error("device scratch too small: %zu bytes given, %zu needed", dev_scratch_bytes, need);
+    return STG_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t s = as_stream(stream);
+  float* dx = static_cast<float*>(dev_scratch);
+  float* dout = dx + nf;
+  float* dns = dout + nf;
+  float* drs = dns + n4;
+  float* des = drs + n4;
+  STG_CUDA(cudaMemcpyAsync(dx, x_host, n * feat * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (nbr_scale_host) STG_CUDA(cudaMemcpyAsync(dns, nbr_scale_host, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (row_scale_host) STG_CUDA(cudaMemcpyAsync(drs, row_scale_host, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (edge_scale_host) STG_CUDA(cudaMemcpyAsync(des, edge_scale_host, e * sizeof(float), cudaMemcpyHostToDevice, s));
+  rc = agg_scaled_sum_device(g, dx, feat, nbr_scale_host ? dns : nullptr, edge_scale_host ? des : nullptr,
+                             row_scale_host ? drs : nullptr, dout, s);
+  if (rc != STG_OK) return rc;
+  STG_CUDA(cudaMemcpyAsync(out_host, dout, n * feat * sizeof(float), cudaMemcpyDeviceToHost, s));
+  STG_CUDA(cudaStreamSynchronize(s));
+  return STG_OK;
+}

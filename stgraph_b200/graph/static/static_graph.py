@@ -1,0 +1,114 @@
+"""Static graphs (mirror of ``stgraph/graph/static/static_graph.py:16-126``).
+
+Same constructor and accessors; the CSR (in-edge) and CSC (out-edge) arrays are
+built by GPU kernels instead of Python tuple sorts + a host loop:
+
+* forward graph: edges sorted by (dst, src), ``eid`` = rank in that order
+  (``static_graph.py:65-72``), rows = destinations;
+* backward graph: ``(src, dst, eid)`` sorted lexicographically
+  (``static_graph.py:75-78``), rows = sources, carrying the forward eids.
+
+Deviations from the reference, all deliberate (traps T7/T8):
+the caller's ``edge_list`` is not sorted in place, and edge lists may also be
+given as ``[E,2]`` numpy / torch arrays (61.9 M Python tuples are not practical).
+``edge_weights`` keep the reference meaning: indexed by the post-sort eid.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ..stgraph_base import STGraphBase
+from .csr import _edges_to_device, build_csr_pair
+
+
+class StaticGraph(STGraphBase):
+    def __init__(self, edge_list, edge_weights, num_nodes: int, device=None) -> None:
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise RuntimeError("stgraph_b200.StaticGraph needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._num_nodes = int(num_nodes)
+
+        src, dst = _edges_to_device(edge_list, self.device)
+        self._forward_graph, self._backward_graph, _, n_unique = build_csr_pair(src, dst, self._num_nodes)
+        # static_graph.py:49 -> len(set(edge_list))
+        self._num_edges = int(n_unique.item())
+        self._forward_graph.prepare_hub_schedule(sync=True)
+        self._backward_graph.prepare_hub_schedule(sync=True)
+
+        self.edge_weights = None
+        if edge_weights is not None and len(edge_weights) > 0:
+            w = torch.as_tensor(np.asarray(edge_weights, dtype=np.float32) if not isinstance(edge_weights, torch.Tensor)
+                                else edge_weights).to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+            if w.shape[0] != self._forward_graph.num_edges:
+                raise ValueError(f"edge_weights has {w.shape[0]} entries for {self._forward_graph.num_edges} edges")
+            self.edge_weights = w
+            wd = torch.empty(self._num_nodes, dtype=torch.float32, device=self.device)
+            _lib.call("stg_weighted_row_degree_f32", self._forward_graph.view(), w.data_ptr(), wd.data_ptr(),
+                      _lib.current_stream_ptr())
+            self._forward_graph.weighted_row_degrees = wd
+        self._get_graph_csr_ptrs()
+
+    def _get_graph_csr_ptrs(self) -> None:
+        f, b = self._forward_graph, self._backward_graph
+        self.fwd_row_offset_ptr = f.row_offset_ptr
+        self.fwd_column_indices_ptr = f.column_indices_ptr
+        self.fwd_eids_ptr = f.eids_ptr
+        self.fwd_node_ids_ptr = f.node_ids_ptr
+        self.bwd_row_offset_ptr = b.row_offset_ptr
+        self.bwd_column_indices_ptr = b.column_indices_ptr
+        self.bwd_eids_ptr = b.eids_ptr
+        self.bwd_node_ids_ptr = b.node_ids_ptr
+
+    def get_num_nodes(self) -> int:
+        return self._num_nodes
+
+    def get_num_edges(self) -> int:
+        return self._num_edges
+
+    def get_ndata(self, field):
+        return self._ndata.get(field, None)
+
+    def set_ndata(self, field: str, val) -> None:
+        self._ndata[field] = val
+
+    def graph_type(self) -> str:
+        return "csr_unsorted"
+
+    def fwd_view(self):
+        return self._forward_graph.view()
+
+    def bwd_view(self):
+        return self._backward_graph.view()
+
+    # ---- degrees: same names / dtypes as the reference (static_graph.py:115-126)
+    def in_degrees(self) -> np.ndarray:
+        return self._forward_graph.row_degrees.cpu().numpy().astype("int32")
+
+    def out_degrees(self) -> np.ndarray:
+        return self._forward_graph.col_degrees.cpu().numpy().astype("int32")
+
+    def weighted_in_degrees(self) -> np.ndarray:
+        wd = self._forward_graph.weighted_row_degrees
+        if wd is None:
+            return np.zeros(self._num_nodes, dtype="int32")
+        return wd.cpu().numpy().astype("int32")   # truncation like np.array(list_of_float, dtype="int32")
+
+    # ---- device-resident helpers (new; keep degrees / norm off the host) ------
+    def in_degrees_tensor(self) -> torch.Tensor:
+        return self._forward_graph.row_degrees
+
+    def out_degrees_tensor(self) -> torch.Tensor:
+        return self._forward_graph.col_degrees
+
+    def degree_norm(self, weighted: bool = False) -> torch.Tensor:
+        """``deg^-0.5`` with inf -> 0 as a ``[N,1]`` fp32 device tensor (``benchmarking/gcn/seastar/train.py:53-57``)."""
+        if weighted and self._forward_graph.weighted_row_degrees is not None:
+            deg = self._forward_graph.weighted_row_degrees.to(torch.int32)
+        else:
+            deg = self._forward_graph.row_degrees
+        norm = torch.empty(self._num_nodes, dtype=torch.float32, device=self.device)
+        _lib.call("stg_degree_norm_f32", deg.data_ptr(), self._num_nodes, norm.data_ptr(), _lib.current_stream_ptr())
+        return norm.unsqueeze(1)

@@ -1,0 +1,85 @@
+"""Thin Python wrappers over the C-ABI kernels (tensor checks + stream plumbing).
+
+Argument validation (dtype, contiguity, device) happens here; the C functions
+validate pointers/sizes and return error codes (SURVEY.md section 8(b) "errors").
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+#: number of kernels launched through this module since import (bench.py reports it)
+launch_count = 0
+
+
+def _check(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (stgraph_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    """``out[r] = row_scale[r] * sum_e nbr_scale[c_e] * edge_scale[eid_e] * x[c_e]`` (see ``stg_agg_scaled_sum_f32``)."""
+    global launch_count
+    _check(x, "x")
+    n = view.num_nodes
+    if x.shape[0] != n:
+        raise ValueError(f"x has {x.shape[0]} rows for a graph of {n} nodes")
+    feat = x.numel() // max(n, 1) if n > 0 else 0
+    for nm, t, cnt in (("nbr_scale", nbr_scale, n), ("row_scale", row_scale, n), ("edge_scale", edge_scale, None)):
+        if t is not None:
+            _check(t, nm)
+            if cnt is not None and t.numel() != cnt:
+                raise ValueError(f"{nm} must have {cnt} elements, got {t.numel()}")
+    if edge_scale is not None and edge_scale.numel() < view.num_edges:
+        raise ValueError(f"edge_scale has {edge_scale.numel()} elements for {view.num_edges} edges")
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _check(out, "out")
+        if out.shape != x.shape:
+            raise ValueError("out must have the shape of x")
+    if n == 0 or feat == 0:
+        return out
+    _lib.call("stg_agg_scaled_sum_f32", ctypes.byref(view), x.data_ptr(), feat, _lib.ptr(nbr_scale),
+              _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(), _lib.current_stream_ptr())
+    launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
+    return out
+
+
+def agg_scaled_sum_host(view: _lib.StgCsrView, x_host: torch.Tensor, out_host: torch.Tensor, scratch: torch.Tensor,
+                        nbr_scale_host=None, edge_scale_host=None, row_scale_host=None):
+    """Host-buffer variant (H2D + kernel + D2H inside one C call); buffers should be pinned."""
+    global launch_count
+    n = view.num_nodes
+    feat = x_host.numel() // max(n, 1)
+    _lib.call("stg_agg_scaled_sum_f32_host", ctypes.byref(view), x_host.data_ptr(), feat,
+              _lib.ptr(nbr_scale_host), _lib.ptr(edge_scale_host), _lib.ptr(row_scale_host),
+              out_host.data_ptr(), scratch.data_ptr(), scratch.numel() * scratch.element_size(),
+              _lib.current_stream_ptr())
+    launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
+    return out_host
+
+
+def host_scratch_bytes(num_nodes: int, num_edges: int, feat: int) -> int:
+    up4 = lambda v: (v + 3) // 4 * 4
+    return 4 * (2 * up4(num_nodes * feat) + 2 * up4(num_nodes) + up4(num_edges))
+
+
+def device_info(device: int = 0):
+    sm = ctypes.c_int32()
+    l2 = ctypes.c_int64()
+    maj = ctypes.c_int32()
+    mnr = ctypes.c_int32()
+    _lib.call("stg_device_info", device, ctypes.byref(sm), ctypes.byref(l2), ctypes.byref(maj), ctypes.byref(mnr))
+    return {"sm_count": sm.value, "l2_bytes": l2.value, "cc": (maj.value, mnr.value)}
