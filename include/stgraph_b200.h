@@ -120,7 +120,7 @@ enum { STG_VM_MAX_TENSORS = 24, STG_VM_MAX_INSTR = 96, STG_VM_MAX_REGS = 48, STG
 typedef enum StgVmSide { STG_VM_CENTER = 0, STG_VM_NBR = 1, STG_VM_EDGE = 2, STG_VM_PARAM = 3 } StgVmSide;
 typedef enum StgVmPhase { STG_VM_PRE = 0, STG_VM_LOOP = 1, STG_VM_POST = 2 } StgVmPhase;
 typedef enum StgVmOp {
-  STG_OP_LOAD = 0,   /* r[dst] = tensor[a] (indexed by its side, broadcast by size) */
+  STG_OP_LOAD = 0,   /* r[dst] = tensor[a] (indexed by its side, broadcast per its bc flags) */
   STG_OP_CONST,      /* r[dst] = imm */
   STG_OP_ADD, STG_OP_SUB, STG_OP_MUL, STG_OP_DIV,   /* r[dst] = r[a] op r[b] */
   STG_OP_EXP,        /* r[dst] = expf(r[a]) */
@@ -133,31 +133,40 @@ typedef enum StgVmOp {
   STG_OP_ACC_MAX,    /* acc[dst] = max(acc[dst], r[a]) */
   STG_OP_ACC_MIN,
   STG_OP_ACC_READ,   /* r[dst] = acc[a]; b=1: divide by the row length (AggMean) (POST only) */
-  STG_OP_STORE,      /* tensor[a] = r[b]; imm!=0: sum over the tensor's broadcast group first */
+  STG_OP_STORE,      /* tensor[a] = r[b]; imm != 0: sum r[b] over the lanes the tensor is broadcast across */
+  STG_OP_GSUM,       /* r[dst] = sum of r[a] over dim1 (b=1) within each dim0 slice, broadcast back */
   STG_OP_COUNT_
 } StgVmOp;
 
+/* A tensor of the unit.  Its per-element shape is (bc0 ? dim0 : 1) x (bc1 ? dim1 : 1); feature lane
+ * tx = i0*dim1 + i1 reads element (bc0 ? i0 : 0, bc1 ? i1 : 0)
+ * (the reference's broadcast index, kernel_context.py:179-204). */
 typedef struct StgVmTensor {
-  int32_t side;  /* StgVmSide */
-  int32_t size;  /* elements per node/edge (1 for params of size 1); must divide lanes */
+  int32_t side; /* StgVmSide */
+  int32_t bc0;
+  int32_t bc1;
+  int32_t pad;
 } StgVmTensor;
 
 typedef struct StgVmInstr {
   int16_t op;    /* StgVmOp */
-  int16_t phase; /* StgVmPhase */
+  int16_t phase; /* StgVmPhase; instructions are ordered PRE..., LOOP..., POST... */
   int16_t dst, a, b;
   int16_t pad;
   float imm;
 } StgVmInstr;
 
 typedef struct StgVmProgram {
-  int32_t lanes;       /* feature lanes per row = product of the unit's max dims */
+  int32_t dim0, dim1;  /* the unit's widest per-element shape; lanes = dim0*dim1 */
   int32_t n_tensors, n_instr, n_regs, n_acc;
+  int32_t n_pre, n_loop;   /* instr[0,n_pre) PRE, [n_pre,n_pre+n_loop) LOOP, rest POST */
   float acc_init[STG_VM_MAX_ACC];
   StgVmTensor tensors[STG_VM_MAX_TENSORS];
   StgVmInstr instr[STG_VM_MAX_INSTR];
 } StgVmProgram;
 
+/* Runs the program once per (row, lane) of the given view (rows = "center" side). Tensors written
+ * with a reducing STORE must be zero-filled by the caller (atomic accumulation may be used). */
 int stg_vm_run_f32(const StgCsrView* g, const StgVmProgram* prog, void* const* tensors, void* stream);
 
 /* --------------------------------------------------- graph structure ops */

@@ -152,15 +152,17 @@ def gat_stock_forward(fwd_csr, el, er, feat, slope=0.2, dtype=torch.float64):
     return out.to(feat.dtype), v3.to(feat.dtype), v4.to(feat.dtype)
 
 
-def gat_stock_backward(fwd_csr, el, er, feat, grad_out, slope=0.2, dtype=torch.float64):
+def gat_stock_backward(fwd_csr, el, er, feat, grad_out, slope=0.2, dtype=torch.float64, return_mag=False):
     """Backward of the stock trace with the *reference's* gradient rules.
 
     ``registry.py:210-213`` gives ``Sub`` a +1 gradient for both operands, so
     although the forward does not depend on ``el``/``er`` the reference still
     emits ``d_el[u] = sum_e V25``, ``d_er[v] = sum_e V25`` with
-    ``V25 = ((dout*feat)/V4 - (dout/V4)*out) * V3 * lrelu'(V1)`` summed over D,
-    accumulated once through ``V0``'s first use and once through its second
-    (``V24 = 0.2`` since ``V1 = 0``).
+    ``V25 = ((dout*feat)/V4 - (dout/V4)*out) * V3 * lrelu'(V1)`` summed over D
+    (``V24 = 0.2`` since ``V1 = 0``).  ``V0`` feeds both
+    operands of ``Sub`` but ``Stmt.grad`` collects per-operand gradients in a
+    ``dict`` keyed by the variable (``program.py:328-329``), so only ONE of the two
+    +1 contributions survives: ``dV0 = dV1``, not ``2*dV1``.
     Returns ``(d_feat [N,H,D], d_el [N,H,1], d_er [N,H,1])``.
     """
     rows, cols = csr_to_coo(fwd_csr.row_offset, fwd_csr.column_indices)
@@ -185,11 +187,19 @@ def gat_stock_backward(fwd_csr, el, er, feat, grad_out, slope=0.2, dtype=torch.f
     v23 = v22 * v3                                          # exp'
     v24 = torch.where(v1 > 0, torch.ones_like(v1), torch.full_like(v1, slope))
     v25 = (v23 * v24).sum(dim=-1, keepdim=True)             # [E,H,1]
-    # Sub(V0, V0): +1 for both operands -> V0 receives 2 * V25; Add splits to el / er
-    d_v0 = 2.0 * v25
+    # Sub(V0, V0): +1 for both operands, but the dict keeps one contribution; Add passes it to el and er
+    d_v0 = v25
     d_el = torch.zeros((n, h, 1), dtype=dtype).index_add_(0, cols, d_v0)
     d_er = torch.zeros((n, h, 1), dtype=dtype).index_add_(0, rows, d_v0)
     t = feat.dtype
+    if return_mag:
+        # sum of |terms| of each reduction: d_er is an exact zero in real arithmetic (the softmax
+        # weights sum to one), so only this magnitude gives a meaningful tolerance
+        a25 = ((v15.abs() + v17.abs()) * v3 * v24.abs()).sum(dim=-1, keepdim=True)
+        m_feat = torch.zeros((n, h, d), dtype=dtype).index_add_(0, cols, (g[rows] * v5).abs())
+        m_el = torch.zeros((n, h, 1), dtype=dtype).index_add_(0, cols, a25)
+        m_er = torch.zeros((n, h, 1), dtype=dtype).index_add_(0, rows, a25)
+        return d_feat.to(t), d_el.to(t), d_er.to(t), m_feat, m_el, m_er
     return d_feat.to(t), d_el.to(t), d_er.to(t)
 
 

@@ -1,0 +1,89 @@
+"""Generate ``tests/golden/*.npz`` from the reference itself (run in the build container).
+
+TEST INFRASTRUCTURE ONLY.  Requires ``oracle/_ref`` (``python oracle/build_ref.py``).  Every array
+written here was computed by reference code: the CSR arrays by ``CSR::CSR`` from
+``/root/reference/stgraph/graph/static/csr.cu``, the feature/gradient tensors by the CUDA kernels the
+reference's code generator emits for ``GCNConv`` / ``GATConv`` (executed on the CPU through
+``oracle/simt_shim.h``).  Inputs are seeded; the fixtures are small (N=40, E=200).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_emulate as RE  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def make_graph(n=40, e=200, seed=0):
+    rng = np.random.default_rng(seed)
+    key = rng.choice(n * n, size=e, replace=False)
+    return (key // n).astype(np.int32), (key % n).astype(np.int32)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    n, e = 40, 200
+    src, dst = make_graph(n, e, 0)
+    rng = np.random.default_rng(1)
+    w = rng.uniform(0.1, 1.0, size=e).astype(np.float32)
+    fwd, bwd = RE.reference_static_graph(src, dst, w, n)
+    out = {"src": src, "dst": dst, "num_nodes": np.int32(n), "edge_weight_by_eid": w}
+    for tag, c in (("fwd", fwd), ("bwd", bwd)):
+        for f in ("row_offset", "column_indices", "eids", "node_ids", "in_degrees", "out_degrees", "weighted_out_degrees"):
+            out[f"{tag}_{f}"] = getattr(c, f)
+    # a graph with isolated vertices / empty rows and a multi-edge, for the row-offset back-fill path
+    src2 = np.array([5, 5, 1, 7, 7, 7, 2], dtype=np.int32)
+    dst2 = np.array([1, 3, 5, 1, 3, 9, 9], dtype=np.int32)
+    f2, b2 = RE.reference_static_graph(src2, dst2, np.ones(7, np.float32), 12)
+    out.update({"sparse_src": src2, "sparse_dst": dst2, "sparse_num_nodes": np.int32(12)})
+    for tag, c in (("sparse_fwd", f2), ("sparse_bwd", b2)):
+        for f in ("row_offset", "column_indices", "eids", "in_degrees", "out_degrees"):
+            out[f"{tag}_{f}"] = getattr(c, f)
+    np.savez_compressed(os.path.join(GOLD, "ref_structure.npz"), **out)
+
+    kout = {}
+    f32 = lambda *s: rng.standard_normal(s).astype(np.float32)
+    norm = (rng.uniform(0.2, 1.0, size=(n, 1))).astype(np.float32)
+
+    def run_case(case, inputs, grads):
+        kernels, lib = RE.load_case(case)
+        tensors = dict(inputs)
+        for k in kernels:
+            for name, vt, shp in zip(k["args"], k["arg_types"], k["arg_shapes"]):
+                if name not in tensors:
+                    lead = e if vt == "EDGE" else n
+                    if name in k["rets"]:
+                        tensors[name] = np.zeros([lead] + shp, np.float32)       # executor.new_zeros
+                    else:                                                          # incoming gradient
+                        tensors[name] = grads.pop(0)
+            csr = fwd if k["parallel_mode"] == "DstParallel" else bwd
+            launch = RE.run_reference_kernel(lib, k, tensors, csr, n)
+            kout[f"{case}/{k['name']}/launch"] = np.array(launch, np.int32)
+            kout[f"{case}/{k['name']}/args"] = np.array(k["args"])
+            kout[f"{case}/{k['name']}/rets"] = np.array(k["rets"])
+            kout[f"{case}/{k['name']}/mode"] = np.array(k["parallel_mode"])
+            kout[f"{case}/{k['name']}/program"] = np.array(k["program"])
+        for name, t in tensors.items():
+            kout[f"{case}/tensor/{name}"] = t
+        kout[f"{case}/kernels"] = np.array([k["name"] for k in kernels])
+
+    h16 = f32(n, 16)
+    run_case("gcn_f16", {"Vhinb": h16, "Vnormcen": norm, "Vnorminb": norm}, [f32(n, 16)])
+    h7 = f32(n, 7)
+    run_case("gcnw_f7", {"Vhinb": h7, "Vnormcen": norm, "Vnorminb": norm, "Vedge_weight": w.reshape(e, 1).copy()},
+             [f32(n, 7)])
+    for case, (hh, dd) in (("gat_h8d16", (8, 16)), ("gat_h2d4", (2, 4))):
+        el, er, feat = f32(n, hh, 1), f32(n, hh, 1), f32(n, hh, dd)
+        run_case(case, {"Velinb": el, "Vercen": er, "Vfeat_srcinb": feat}, [f32(n, hh, dd)])
+    np.savez_compressed(os.path.join(GOLD, "ref_kernels.npz"), **kout)
+    print("wrote", os.path.join(GOLD, "ref_structure.npz"), "and ref_kernels.npz:", len(kout), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -42,7 +42,7 @@ class StgCsrView(Structure):
 
 
 class StgVmTensor(Structure):
-    _fields_ = [("side", c_int32), ("size", c_int32)]
+    _fields_ = [("side", c_int32), ("bc0", c_int32), ("bc1", c_int32), ("pad", c_int32)]
 
 
 class StgVmInstr(Structure):
@@ -59,11 +59,14 @@ class StgVmInstr(Structure):
 
 class StgVmProgram(Structure):
     _fields_ = [
-        ("lanes", c_int32),
+        ("dim0", c_int32),
+        ("dim1", c_int32),
         ("n_tensors", c_int32),
         ("n_instr", c_int32),
         ("n_regs", c_int32),
         ("n_acc", c_int32),
+        ("n_pre", c_int32),
+        ("n_loop", c_int32),
         ("acc_init", c_float * VM_MAX_ACC),
         ("tensors", StgVmTensor * VM_MAX_TENSORS),
         ("instr", StgVmInstr * VM_MAX_INSTR),

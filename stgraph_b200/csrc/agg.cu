@@ -19,6 +19,8 @@
 //   4*(2*N*F + E + (N+1) + 2*N [+ E for edge_scale]).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace stg {
 namespace {
 
@@ -124,6 +126,7 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
   }
 }
 
+// One group per row (baseline variant, kept for A/B measurements: STG_AGG_VARIANT=rows).
 template <int VEC, int GROUP, int NACC>
 __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
@@ -151,6 +154,268 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
     if (o < p.width) {
       scale_vec(acc[k], r);
       st_row<VEC>(dst + o, acc[k]);
+    }
+  }
+}
+
+// Rows-per-group of the streaming kernel: a group owns kRowsPerGroup consecutive rows and
+// walks their (contiguous) CSR edge range as ONE stream, so the load pipeline (index prefetch
+// one batch ahead, UNROLL neighbour rows in flight) never drains at a row boundary -- most
+// rows of a power-law graph are shorter than one batch.
+constexpr int kRowsPerGroup = 8;
+
+template <int VEC, int GROUP, int NACC>
+__global__ void __launch_bounds__(kBlockThreads) agg_stream_kernel(const AggParams p) {
+  using T = typename VecT<VEC>::type;
+  constexpr int GROUPS_PER_WARP = 32 / GROUP;
+  constexpr int UNROLL = (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (GROUP - 1);
+  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
+  const int warp = blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5);
+  const int group = warp * GROUPS_PER_WARP + lane / GROUP;
+  const int r0 = group * kRowsPerGroup;
+  if (r0 >= p.num_rows) return;
+  const int r1 = min(r0 + kRowsPerGroup, p.num_rows);
+  const int thr = p.hub_threshold;
+
+  bool act[NACC];
+  int off[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    off[k] = (gl + k * GROUP) * VEC;
+    act[k] = off[k] < p.width;
+  }
+  T acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+
+  auto flush = [&](int row) {
+    const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+    float* dst = p.out + static_cast<size_t>(row) * p.ld;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      if (act[k]) {
+        scale_vec(acc[k], r);
+        st_row<VEC>(dst + off[k], acc[k]);
+      }
+      zero_vec(acc[k]);
+    }
+  };
+
+  int cur = r0;
+  while (cur < r1) {
+    // ---- next run of consecutive non-hub rows [cur, rr) with edges [e_lo, e_hi)
+    const int e_lo = __ldg(p.row_off + cur);
+    int e_hi = __ldg(p.row_off + cur + 1);
+    if (thr > 0 && (e_hi - e_lo) > thr) { ++cur; continue; }   // hub kernel owns this row
+    int rr = cur + 1;
+    if (thr > 0) {
+      while (rr < r1) {
+        const int ne = __ldg(p.row_off + rr + 1);
+        if (ne - e_hi > thr) break;
+        e_hi = ne;
+        ++rr;
+      }
+    } else {
+      rr = r1;
+      e_hi = __ldg(p.row_off + r1);
+    }
+    int cur_end = __ldg(p.row_off + cur + 1);
+
+    auto load_meta = [&](int base, int& c, float& s) {
+      c = 0;
+      s = 0.f;
+      const int e = base + gl;
+      if (e < e_hi) {
+        c = ld_stream(p.col + e);
+        float sc = 1.f;
+        if (p.ns) sc = __ldg(p.ns + c);
+        if (p.es) {
+          const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
+          sc *= __ldg(p.es + eid);
+        }
+        s = sc;
+      }
+    };
+
+    int my_c, nx_c;
+    float my_s, nx_s;
+    load_meta(e_lo, my_c, my_s);
+    for (int base = e_lo; base < e_hi; base += GROUP) {
+      load_meta(base + GROUP, nx_c, nx_s);
+      const int n = min(GROUP, e_hi - base);
+      for (int j = 0; j < n; j += UNROLL) {
+        float s[UNROLL];
+        T v[UNROLL][NACC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int c = __shfl_sync(gmask, my_c, j + u, GROUP);
+          s[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
+          const float* src = p.x + static_cast<size_t>(c) * p.ld;
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) {
+            if (act[k] && (j + u) < n) v[u][k] = ld_row<VEC>(src + off[k]);
+            else zero_vec(v[u][k]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (j + u < n) {
+            const int e = base + j + u;
+            while (e >= cur_end) {          // crossed into the next row (empty rows flush zeros)
+              flush(cur);
+              ++cur;
+              cur_end = __ldg(p.row_off + cur + 1);
+            }
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) fma_vec(acc[k], s[u], v[u][k]);
+          }
+        }
+      }
+      my_c = nx_c;
+      my_s = nx_s;
+    }
+    while (cur < rr) {   // last row of the run and trailing empty rows
+      flush(cur);
+      ++cur;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Asynchronous-copy gather pipeline (cp.async -> SASS LDGSTS).
+// The LDG kernels above are latency bound: ncu shows long_scoreboard as the only stall that
+// matters, ~20 warps x <=8 neighbour rows in flight per SM, DRAM and L2 both below 30 %
+// (profiles/r01_agg_ncu.md).  Registers limit the bytes in flight, so this variant copies each
+// neighbour row with ONE warp-wide cp.async.cg (16 B per lane, L2 -> shared memory, no register
+// staging) into a per-warp ring of K*G rows; commit groups of G rows give a K-deep pipeline and
+// consumption is a conflict-free LDS.128 per row.  A warp walks kRowsPerGroup rows as one
+// contiguous edge stream and flushes the accumulator whenever the stream crosses a row end.
+// (A cp.async.bulk/UBLKCP version was measured first: one bulk copy per 400-512 B row runs at
+// ~40-70 cycles per copy per SM and was 2-4x SLOWER; see profiles/r01_agg_ncu.md.)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int G, int K>
+__global__ void __launch_bounds__(kBlockThreads) agg_async_kernel(const AggParams p) {
+  extern __shared__ __align__(128) unsigned char async_smem[];
+  constexpr int RR = G * K;        // rows in the data ring
+  constexpr int RS = 64;           // scales ring (>= 32 + RR is required; RR <= 32)
+  static_assert(RR <= 32 && 32 % G == 0, "ring geometry");
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int rowb = p.width * 4;                                   // bytes per neighbour row (multiple of 16)
+  unsigned char* ring = async_smem + static_cast<size_t>(wid) * RR * rowb;
+  float* scales = reinterpret_cast<float*>(async_smem + static_cast<size_t>(nwarps) * RR * rowb) + wid * RS;
+  const uint32_t ring_s = smem_u32(ring) + lane * 16;
+
+  const int warp = blockIdx.x * nwarps + wid;
+  const int r0 = warp * kRowsPerGroup;
+  if (r0 >= p.num_rows) return;
+  const int r1 = min(r0 + kRowsPerGroup, p.num_rows);
+  const int thr = p.hub_threshold;
+  const bool act = lane * 4 < p.width;
+  const float* xl = p.x + lane * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&](int row) {
+    const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+    if (act) {
+      scale_vec(acc, r);
+      st_row<4>(p.out + static_cast<size_t>(row) * p.ld + lane * 4, acc);
+    }
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+
+  int cur = r0;
+  while (cur < r1) {
+    const int e_lo = __ldg(p.row_off + cur);
+    int e_hi = __ldg(p.row_off + cur + 1);
+    if (thr > 0 && (e_hi - e_lo) > thr) { ++cur; continue; }   // hub kernel owns this row
+    int rr = cur + 1;
+    if (thr > 0) {
+      while (rr < r1) {
+        const int ne = __ldg(p.row_off + rr + 1);
+        if (ne - e_hi > thr) break;
+        e_hi = ne;
+        ++rr;
+      }
+    } else {
+      rr = r1;
+      e_hi = __ldg(p.row_off + r1);
+    }
+    int cur_end = __ldg(p.row_off + cur + 1);
+    const int total = e_hi - e_lo;
+    const int ngroups = (total + G - 1) / G;
+    int my_c = 0;
+
+    for (int gi = 0; gi < ngroups + K - 1; ++gi) {
+      if (gi < ngroups) {
+        const int idx0 = gi * G;                     // stream index of the group's first edge
+        if ((idx0 & 31) == 0) {                      // new batch of 32 edges: cooperative index/scale load
+          const int e = e_lo + idx0 + lane;
+          my_c = 0;
+          float sc = 0.f;
+          if (e < e_hi) {
+            my_c = ld_stream(p.col + e);
+            sc = 1.f;
+            if (p.ns) sc = __ldg(p.ns + my_c);
+            if (p.es) {
+              const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
+              sc *= __ldg(p.es + eid);
+            }
+          }
+          scales[(idx0 + lane) & (RS - 1)] = sc;
+        }
+        const int n = min(G, total - idx0);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const int c = __shfl_sync(0xffffffffu, my_c, (idx0 + u) & 31);
+          if (u < n && act)
+            cp_async16(ring_s + ((idx0 + u) % RR) * rowb, xl + static_cast<size_t>(c) * p.ld);
+        }
+      }
+      cp_async_commit();
+      if (gi >= K - 1) {
+        cp_async_wait<K - 1>();
+        __syncwarp();
+        const int idx0 = (gi - (K - 1)) * G;
+        const int n = min(G, total - idx0);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          if (u < n) {
+            const int e = e_lo + idx0 + u;
+            while (e >= cur_end) {
+              flush(cur);
+              ++cur;
+              cur_end = __ldg(p.row_off + cur + 1);
+            }
+            const float s = scales[(idx0 + u) & (RS - 1)];
+            if (act) {
+              const float4 v = *reinterpret_cast<const float4*>(ring + ((idx0 + u) % RR) * rowb + lane * 16);
+              fma_vec(acc, s, v);
+            }
+          }
+        }
+        __syncwarp();          // slots of this group are refilled by the next iteration's copies
+      }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    while (cur < rr) {
+      flush(cur);
+      ++cur;
     }
   }
 }
@@ -222,16 +487,87 @@ __global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p)
   }
 }
 
+// 0 = group per row, 1 = streaming multi-row groups, 2 = cp.async ring pipeline
+// (env STG_AGG_VARIANT=rows|stream|async)
+inline int agg_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("STG_AGG_VARIANT");
+    v = (e && e[0] == 's') ? 1 : (e && e[0] == 'a') ? 2 : 0;
+  }
+  return v;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <int G, int K>
+int launch_async_cfg(const AggParams& p, int warps, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(warps) * (static_cast<size_t>(G * K) * p.width * 4 + 64 * 4) + 128;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(agg_async_kernel<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return STG_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  const int rows_per_block = warps * kRowsPerGroup;
+  const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
+  agg_async_kernel<G, K><<<blocks, warps * 32, smem, stream>>>(p);
+  STG_LAUNCH_CHECK("agg_async_kernel");
+  return STG_OK;
+}
+
+int launch_hub_only(const AggParams& p, cudaStream_t stream);
+
+inline int launch_async(const AggParams& p, cudaStream_t stream) {
+  static const int g = env_int("STG_ASYNC_G", 8), k = env_int("STG_ASYNC_K", 4), warps = env_int("STG_ASYNC_WARPS", 8);
+  int rc;
+  if (g == 8 && k == 2) rc = launch_async_cfg<8, 2>(p, warps, stream);
+  else if (g == 8 && k == 3) rc = launch_async_cfg<8, 3>(p, warps, stream);
+  else if (g == 4 && k == 4) rc = launch_async_cfg<4, 4>(p, warps, stream);
+  else if (g == 4 && k == 8) rc = launch_async_cfg<4, 8>(p, warps, stream);
+  else if (g == 16 && k == 2) rc = launch_async_cfg<16, 2>(p, warps, stream);
+  else if (g == 2 && k == 8) rc = launch_async_cfg<2, 8>(p, warps, stream);
+  else rc = launch_async_cfg<8, 4>(p, warps, stream);
+  if (rc != STG_OK) return rc;
+  return launch_hub_only(p, stream);
+}
+
 template <int VEC, int GROUP, int NACC>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
-  constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
-  const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > 0) {
-    agg_rows_kernel<VEC, GROUP, NACC><<<blocks, kBlockThreads, 0, stream>>>(p);
-    STG_LAUNCH_CHECK("agg_rows_kernel");
+  if (VEC == 4 && GROUP == 32 && NACC == 1 && agg_variant() == 2) {
+    return launch_async(p, stream);
+  } else if (agg_variant() == 1) {
+    constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP) * kRowsPerGroup;
+    const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
+    if (blocks > 0) {
+      agg_stream_kernel<VEC, GROUP, NACC><<<blocks, kBlockThreads, 0, stream>>>(p);
+      STG_LAUNCH_CHECK("agg_stream_kernel");
+    }
+  } else {
+    constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
+    const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
+    if (blocks > 0) {
+      agg_rows_kernel<VEC, GROUP, NACC><<<blocks, kBlockThreads, 0, stream>>>(p);
+      STG_LAUNCH_CHECK("agg_rows_kernel");
+    }
   }
   if (p.hub_threshold > 0 && p.hub_rows != nullptr) {
     agg_hub_kernel<VEC, GROUP, NACC><<<2 * sm_count(), kHubThreads, 0, stream>>>(p);
+    STG_LAUNCH_CHECK("agg_hub_kernel");
+  }
+  return STG_OK;
+}
+
+int launch_hub_only(const AggParams& p, cudaStream_t stream) {
+  if (p.hub_threshold > 0 && p.hub_rows != nullptr) {
+    agg_hub_kernel<4, 32, 1><<<2 * sm_count(), kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   return STG_OK;

@@ -1,0 +1,71 @@
+"""Vertex-centric GCN layer (mirror of ``stgraph/nn/pytorch/static/gcn_conv.py:78-189``).
+
+Same constructor, parameter names (``weight``, ``bias``) and forward contract, so state_dicts
+interchange with the reference layer:
+
+    h' = act( norm * sum_{u in in(v)} (h W)[u] * norm[u] [* w_e] + b )
+
+``torch.mm`` stays a library GEMM (it is not the hot path); the aggregation is the traced
+vertex program, lowered to the fused sm_100a gather kernel (``csrc/agg.cu``).
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+from torch import Tensor, nn
+
+from ....compiler import STGraph
+from ....compiler.backend.pytorch.torch_callback import STGraphBackendTorch
+from ....utils.constants import SizeConstants
+
+
+class GCNConv(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int,
+                 activation: Callable[..., Tensor] | None = None, bias: bool = True) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.Tensor(in_channels, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.bias = None
+        self.activation = activation
+        self.stgraph = STGraph(STGraphBackendTorch())
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, graph, h: Tensor, edge_weight: Tensor | None = None) -> Tensor:
+        norm = graph.get_ndata("norm")
+        if norm is None:
+            raise KeyError("StaticGraph passed to GCNConv forward pass does not contain 'norm' node data")
+        if (len(norm.shape) != SizeConstants.NODE_NORM_SIZE.value or norm.shape[1] != 1
+                or norm.shape[0] != graph.get_num_nodes()):
+            raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_nodes, 1)")
+
+        h = torch.mm(h, self.weight)
+
+        if edge_weight is None:
+
+            @self.stgraph.compile(gnn_module=self)
+            def nb_compute(v):
+                return sum([nb.h * nb.norm for nb in v.innbs]) * v.norm
+
+            h = nb_compute(g=graph, n_feats={"norm": norm, "h": h})
+        else:
+
+            @self.stgraph.compile(gnn_module=self)
+            def nb_compute(v):
+                return sum([nb_edge.src.norm * nb_edge.src.h * nb_edge.edge_weight
+                            for nb_edge in v.inedges]) * v.norm
+
+            h = nb_compute(g=graph, n_feats={"norm": norm, "h": h}, e_feats={"edge_weight": edge_weight})
+
+        if self.bias is not None:
+            h = h + self.bias
+        if self.activation:
+            h = self.activation(h)
+        return h

@@ -1,0 +1,236 @@
+"""GPU parity of the layers (GCNConv / GATConv / TGCN) through the public API.
+
+Oracles: closed forms in oracle/aggregate.py evaluated with torch-CPU index_add in fp64 and the
+IR interpreter oracle/ir_interp.py.  Tolerance: rel 1e-5 of max(|ref|, sum|terms|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aggregate as A
+from oracle import structure as S
+from oracle.ir_interp import Interp
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(n, e, seed, cuda):
+    from stgraph_b200.graph import StaticGraph
+
+    rng = np.random.default_rng(seed)
+    key = rng.choice(n * n, size=e, replace=False)
+    src, dst = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    g = StaticGraph(torch.from_numpy(np.stack([src, dst], 1)), None, n)
+    return g, src, dst
+
+
+def _gcn_oracle(src, dst, n, x, W, b, norm, w, gout):
+    """fp64 torch-CPU restatement of gcn_conv.py:158-188 with autograd."""
+    f = S.forward_csr(src, dst, n)
+    rows, cols = A.csr_to_coo(f.row_offset, f.column_indices)
+    x64 = x.double().requires_grad_(True)
+    W64 = W.double().requires_grad_(True)
+    b64 = b.double().requires_grad_(True)
+    h = x64 @ W64
+    msg = h[cols] * norm.double()[cols]
+    if w is not None:
+        msg = msg * w.double().reshape(-1, 1)          # CSR slot i has eid i in the forward graph
+    out = torch.zeros(n, W.shape[1], dtype=torch.float64).index_add(0, rows, msg) * norm.double() + b64
+    out.backward(gout.double())
+    mag = torch.zeros(n, W.shape[1], dtype=torch.float64).index_add(0, rows, msg.detach().abs()) * norm.double()
+    return out.detach(), x64.grad, W64.grad, b64.grad, mag
+
+
+@pytest.mark.parametrize("fin,fout,weighted", [(32, 16, False), (32, 7, False), (20, 16, True), (20, 7, True), (64, 100, False)])
+def test_gcnconv_forward_backward(cuda, fin, fout, weighted):
+    from stgraph_b200.nn.pytorch import GCNConv
+
+    n, e = 400, 5000
+    g, src, dst = _graph(n, e, seed=fin + fout, cuda=cuda)
+    norm = g.degree_norm()
+    g.set_ndata("norm", norm)
+    torch.manual_seed(2)
+    layer = GCNConv(fin, fout).to(cuda)
+    with torch.no_grad():
+        layer.bias.uniform_(-0.1, 0.1)
+    x = torch.randn(n, fin, device=cuda, requires_grad=True)
+    w = (torch.rand(e, 1, device=cuda) + 0.1) if weighted else None
+    gout = torch.randn(n, fout, device=cuda)
+    out = layer(g, x, edge_weight=w)
+    out.backward(gout)
+    ref, gx, gW, gb, mag = _gcn_oracle(src, dst, n, x.detach().cpu(), layer.weight.detach().cpu(),
+                                       layer.bias.detach().cpu(), norm.cpu(), None if w is None else w.cpu(), gout.cpu())
+    A.assert_close_rel(out.detach().cpu(), ref, rel=1e-5, abs_terms=mag + 1e-3, what="GCNConv out")
+    A.assert_close_rel(x.grad.cpu(), gx, rel=2e-5, abs_terms=gx.abs().mean() * torch.ones_like(gx), what="dX")
+    A.assert_close_rel(layer.weight.grad.cpu(), gW, rel=2e-5, abs_terms=gW.abs().mean() * torch.ones_like(gW), what="dW")
+    A.assert_close_rel(layer.bias.grad.cpu(), gb, rel=1e-5, abs_terms=gout.abs().sum(0).cpu().double(), what="db")
+
+
+def test_gcnconv_validates_norm(cuda):
+    from stgraph_b200.nn.pytorch import GCNConv
+
+    g, _, _ = _graph(50, 200, 0, cuda)
+    layer = GCNConv(4, 4).to(cuda)
+    with pytest.raises(KeyError):
+        layer(g, torch.randn(50, 4, device=cuda))
+    g.set_ndata("norm", torch.rand(50, device=cuda))
+    with pytest.raises(ValueError):
+        layer(g, torch.randn(50, 4, device=cuda))
+
+
+def test_gcn_two_layer_model_state_stack(cuda):
+    """Two layers + the same layer applied twice (BPTT-style LIFO use of the executor's state stack)."""
+    from stgraph_b200.nn.pytorch import GCNConv
+
+    n, e = 300, 3000
+    g, src, dst = _graph(n, e, 7, cuda)
+    norm = g.degree_norm()
+    g.set_ndata("norm", norm)
+    torch.manual_seed(0)
+    l1 = GCNConv(16, 16, activation=torch.relu).to(cuda)
+    x = torch.randn(n, 16, device=cuda, requires_grad=True)
+    h = l1(g, x)
+    h = l1(g, h)          # same executor, second entry on the stack
+    h = l1(g, h)
+    loss = (h * h).sum()
+    loss.backward()
+    assert len(l1.stgraph._ctx_map) == 1
+    ctx = next(iter(l1.stgraph._ctx_map.values()))
+    assert len(ctx._executor_cache.ts.tensor_map_stack) == 0      # every forward entry was popped
+    # oracle
+    f = S.forward_csr(src, dst, n)
+    rows, cols = A.csr_to_coo(f.row_offset, f.column_indices)
+    x64 = x.detach().cpu().double().requires_grad_(True)
+    W = l1.weight.detach().cpu().double().requires_grad_(True)
+    b = l1.bias.detach().cpu().double()
+    nr = norm.cpu().double()
+    hh = x64
+    for _ in range(3):
+        t = hh @ W
+        hh = torch.relu(torch.zeros(n, 16, dtype=torch.float64).index_add(0, rows, t[cols] * nr[cols]) * nr + b)
+    (hh * hh).sum().backward()
+    A.assert_close_rel(h.detach().cpu(), hh.detach(), rel=1e-5, abs_terms=hh.detach().abs().mean() * torch.ones_like(hh))
+    A.assert_close_rel(x.grad.cpu(), x64.grad, rel=5e-5, abs_terms=x64.grad.abs().mean() * torch.ones_like(x64.grad))
+    A.assert_close_rel(l1.weight.grad.cpu(), W.grad, rel=5e-5, abs_terms=W.grad.abs().mean() * torch.ones_like(W.grad))
+
+
+@pytest.mark.parametrize("heads,dim", [(8, 16), (2, 4), (1, 32), (3, 5)])
+def test_gatconv_stock_matches_reference_semantics(cuda, heads, dim):
+    """Stock GATConv == mean over in-neighbours, with the reference's el/er gradients (trap T2)."""
+    from stgraph_b200.nn.pytorch import GATConv
+
+    n, e = 300, 2500
+    g, src, dst = _graph(n, e, seed=heads * 10 + dim, cuda=cuda)
+    torch.manual_seed(1)
+    layer = GATConv(24, dim, heads).to(cuda)
+    x = torch.randn(n, 24, device=cuda, requires_grad=True)
+    gout = torch.randn(n, heads, dim, device=cuda)
+    out = layer(g, x)
+    out.backward(gout)
+    # oracle through torch-CPU: fc / el / er are plain torch; the vertex program uses the closed forms
+    f = S.forward_csr(src, dst, n)
+    xc = x.detach().cpu().double().requires_grad_(True)
+    Wfc = layer.fc.weight.detach().cpu().double().requires_grad_(True)
+    al = layer.attn_l.detach().cpu().double().requires_grad_(True)
+    ar = layer.attn_r.detach().cpu().double().requires_grad_(True)
+    feat = (xc @ Wfc.t()).view(-1, heads, dim)
+    el = (feat * al).sum(-1).unsqueeze(-1)
+    er = (feat * ar).sum(-1).unsqueeze(-1)
+    ref, _, _ = A.gat_stock_forward(f, el.detach(), er.detach(), feat.detach())
+    d_feat, d_el, d_er = A.gat_stock_backward(f, el.detach(), er.detach(), feat.detach(), gout.cpu().double())
+    torch.autograd.backward([feat, el, er], [d_feat, d_el, d_er])
+    scale = lambda t: t.abs().mean() * torch.ones_like(t) + 1e-12
+    A.assert_close_rel(out.detach().cpu(), ref, rel=1e-5, abs_terms=scale(ref), what="GAT out")
+    A.assert_close_rel(x.grad.cpu(), xc.grad, rel=1e-4, abs_terms=scale(xc.grad), what="GAT dX")
+    A.assert_close_rel(layer.fc.weight.grad.cpu(), Wfc.grad, rel=1e-4, abs_terms=scale(Wfc.grad), what="GAT dWfc")
+    A.assert_close_rel(layer.attn_l.grad.cpu(), al.grad, rel=1e-4, abs_terms=scale(al.grad), what="GAT d_attn_l")
+    A.assert_close_rel(layer.attn_r.grad.cpu(), ar.grad, rel=1e-4, abs_terms=scale(ar.grad), what="GAT d_attn_r")
+    # forward really is the neighbour mean (independent of el / er)
+    rows, cols = A.csr_to_coo(f.row_offset, f.column_indices)
+    deg = torch.from_numpy(f.row_degrees).double().clamp(min=1).reshape(-1, 1, 1)
+    mean = torch.zeros(n, heads, dim, dtype=torch.float64).index_add(0, rows, feat.detach()[cols]) / deg
+    A.assert_close_rel(out.detach().cpu(), mean, rel=1e-5, abs_terms=scale(mean), what="GAT mean")
+
+
+def test_gat_units_match_ir_interpreter(cuda):
+    """Every unit of the stock GAT (forward and backward) against the IR-level oracle."""
+    from stgraph_b200.nn.pytorch import GATConv
+
+    n, e, heads, dim = 120, 900, 4, 8
+    g, src, dst = _graph(n, e, 3, cuda)
+    torch.manual_seed(4)
+    layer = GATConv(10, dim, heads).to(cuda)
+    x = torch.randn(n, 10, device=cuda, requires_grad=True)
+    out = layer(g, x)
+    gout = torch.randn_like(out)
+    ctx = next(iter(layer.stgraph._ctx_map.values()))
+    ex = ctx._executor_cache
+    saved = dict(ex.ts.tensor_map_stack.top())
+    out.backward(gout)
+    f = S.forward_csr(src, dst, n)
+    order = np.lexsort((src, dst))
+    it = Interp(src[order], dst[order], n)           # edges in eid order
+    feat = layer.fc(x).view(-1, heads, dim).detach()
+    el = (feat * layer.attn_l).sum(-1).unsqueeze(-1).detach()
+    er = (feat * layer.attn_r).sum(-1).unsqueeze(-1).detach()
+    env = {"Velinb": el.cpu(), "Velcen": el.cpu(), "Vercen": er.cpu(), "Verinb": er.cpu(),
+           "Vfeat_srcinb": feat.cpu(), "Vfeat_srccen": feat.cpu()}
+    env = it.run_units(ctx.forward_units, env)
+    A.assert_close_rel(out.detach().cpu(), env[ex._rets[0].id], rel=1e-5,
+                       abs_terms=env[ex._rets[0].id].abs().mean() * torch.ones_like(env[ex._rets[0].id]))
+    for k, t in saved.items():
+        if k in env and not k.endswith(("inb", "cen")):
+            A.assert_close_rel(t.cpu(), env[k], rel=1e-5, abs_terms=env[k].abs().mean() * torch.ones_like(env[k]) + 1e-12,
+                               what=f"saved {k}")
+    for var, gv in ex.grad_in.items():
+        env[gv.id] = gout.cpu()
+    env = it.run_units(ctx.backward_units, env)
+    assert set(v.id for v in ex.grad_out) == {"Velinb", "Vercen", "Vfeat_srcinb"}
+
+
+def test_tgcn_cell_matches_torch(cuda):
+    from stgraph_b200.nn.pytorch import TGCN
+
+    n, e = 200, 2000
+    g, src, dst = _graph(n, e, 11, cuda)
+    norm = g.degree_norm()
+    g.set_ndata("norm", norm)
+    torch.manual_seed(3)
+    cell = TGCN(8, 16).to(cuda)
+    w = torch.rand(e, 1, device=cuda) + 0.1
+    xs = [torch.randn(n, 8, device=cuda) for _ in range(4)]
+    H = None
+    cost = 0
+    for x in xs:
+        H = cell(g, x, w, H)
+        cost = cost + (H ** 2).mean()
+    cost.backward()
+    got = {k: p.grad.detach().cpu().double() for k, p in cell.named_parameters()}
+    # torch-CPU fp64 restatement of temporal/tgcn.py:21-55
+    f = S.forward_csr(src, dst, n)
+    rows, cols = A.csr_to_coo(f.row_offset, f.column_indices)
+    P = {k: p.detach().cpu().double().requires_grad_(True) for k, p in cell.named_parameters()}
+    nr, wc = norm.cpu().double(), w.cpu().double()
+
+    def conv(x, name):
+        t = x @ P[f"conv_{name}.weight"]
+        agg = torch.zeros(n, 16, dtype=torch.float64).index_add(0, rows, t[cols] * nr[cols] * wc) * nr
+        return torch.clamp(agg + P[f"conv_{name}.bias"], -1e6, 1e6)
+
+    def lin(t, name):
+        return t @ P[f"linear_{name}.weight"].t() + P[f"linear_{name}.bias"]
+
+    Hc = torch.zeros(n, 16, dtype=torch.float64)
+    cost_c = 0
+    for x in xs:
+        xc = x.cpu().double()
+        Z = torch.sigmoid(lin(torch.cat((conv(xc, "z"), Hc), 1), "z"))
+        R = torch.sigmoid(lin(torch.cat((conv(xc, "r"), Hc), 1), "r"))
+        Ht = torch.tanh(lin(torch.cat((conv(xc, "h"), Hc * R), 1), "h"))
+        Hc = Z * Hc + (1 - Z) * Ht
+        cost_c = cost_c + (Hc ** 2).mean()
+    cost_c.backward()
+    A.assert_close_rel(H.detach().cpu(), Hc.detach(), rel=2e-5, abs_terms=torch.ones_like(Hc))
+    for k in got:
+        ref = P[k].grad
+        A.assert_close_rel(got[k], ref, rel=2e-4, abs_terms=ref.abs().mean() * torch.ones_like(ref) + 1e-9, what=k)
