@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused GCN neighbour aggregation (forward + backward) on the
+ogbn-products-shaped synthetic graph of BASELINE.json (config 5: 2,449,029 V / 61,859,140 E, F=100).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference ...                     # CPU reference (torch index_add), rank 0 only
+
+One step = one forward aggregation over the in-edge CSR + one backward aggregation over the
+out-edge CSR ("primary measurement = the F=100 aggregation fwd+bwd").
+``value`` = algorithmic bytes of the whole job / max-over-ranks device time (GB/s); ``e2e`` = the same
+through the C-ABI host-buffer entry point with H2D/D2H inside the timed region; ``roofline`` = the
+forward kernel against the measured HBM peak; ``cpu_baseline`` = the oracle port on the host cores.
+At N>1 the graph is row-partitioned (edge-balanced) and feature rows are exchanged over NCCL each
+aggregation (strong scaling: total work fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "gcn_fused_aggregation_fwd_bwd_algorithmic_hbm_gbs"
+UNIT = "GB/s"
+FEAT = 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("STG_BENCH_SCALE", "1.0")),
+                    help="shrink the graph (debug only; the judged number is scale=1)")
+    ap.add_argument("--locality", type=float, default=0.9)
+    ap.add_argument("--window", type=int, default=8192)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / e2e / locality-free legs")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("agg_rows_kernel_fwd_dram_bytes_per_launch")
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args, dev):
+    from stgraph_b200.utils import synthetic
+
+    d = synthetic.products_shaped(seed=0, device=dev, scale=args.scale, locality=args.locality, window=args.window)
+    return d
+
+
+def cpu_reference_sample(src, dst, n, feat, budget_edges=4_000_000, reps=3, threads=None):
+    """torch-CPU index_add of the same vertex program on the first rows holding ~budget_edges edges."""
+    import numpy as np
+
+    from oracle import aggregate as A
+    from oracle import structure as S
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    src, dst = src.cpu().numpy(), dst.cpu().numpy()
+    e_full = src.shape[0]
+    indeg = np.bincount(dst, minlength=n)
+    ro = np.concatenate([[0], np.cumsum(indeg)])
+    rows = int(np.searchsorted(ro, min(budget_edges, e_full), side="left"))
+    rows = max(1, min(rows, n))
+    keep = dst < rows
+    f = S.forward_csr(src[keep], dst[keep], n)
+    e_s = int(keep.sum())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, feat, generator=g)
+    norm = torch.rand(n, generator=g) + 0.5
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        A.scaled_sum(f.row_offset, f.column_indices, f.eids, x, norm, None, norm, dtype=torch.float32)
+        times.append(time.perf_counter() - t0)
+    return min(times), e_s, e_full, rows, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's GPU-only path restated as torch-CPU index_add, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from stgraph_b200.utils import synthetic
+
+    d = synthetic.products_shaped(seed=0, device="cpu", scale=min(args.scale, 0.25), locality=args.locality,
+                                  window=args.window)
+    n_full, e_full = int(2449029 * args.scale), int(61859140 * args.scale) // 2 * 2
+    n = d["num_nodes"]
+    b_full = 2 * synthetic.gcn_algorithmic_bytes(n_full, e_full, FEAT)
+    ts = []
+    e_s = rows = threads = None
+    for i in range(args.warmup + args.steps):
+        t, e_s, e_samp_full, rows, threads = cpu_reference_sample(d["src"], d["dst"], n, FEAT, budget_edges=3_000_000,
+                                                                  reps=1)
+        if i >= args.warmup:
+            ts.append(t)
+    t_step = sum(ts) / len(ts)
+    # one sample = forward aggregation of e_s edges; a full step is fwd+bwd over e_full edges
+    value = b_full * (e_s / (2.0 * e_full)) / t_step / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config5 ogbn-products-shaped GCN aggregation F=100, CPU sample",
+                       "sample_edges": e_s, "sample_rows": rows},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"forward aggregation of the first {rows} destination rows ({e_s} edges, F={FEAT}) "
+                                       f"of a {n}-node graph from the same generator; throughput scaled by edge share"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stgraph_b200 import kernels
+    from stgraph_b200.dist import PartitionedGraph, exchange_rows
+    from stgraph_b200.graph import StaticGraph
+    from stgraph_b200.utils import synthetic
+
+    d = make_workload(args, dev)
+    if world > 1:   # every rank must hold the same graph: rank 0's
+        dist.broadcast(d["src"], src=0)
+        dist.broadcast(d["dst"], src=0)
+    n, e = d["num_nodes"], int(d["src"].shape[0])
+    graph = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, n)
+    norm = graph.degree_norm().reshape(-1).contiguous()
+    gen = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, FEAT, device=dev, generator=gen)
+    gout = torch.randn(n, FEAT, device=dev, generator=gen)
+    b_alg_one = synthetic.gcn_algorithmic_bytes(n, e, FEAT)
+    b_alg_step = 2 * b_alg_one
+
+    if world > 1:
+        pg = PartitionedGraph(graph, rank, world)
+        f_lo, f_hi = pg.local_rows("fwd")
+        b_lo, b_hi = pg.local_rows("bwd")
+        out_f = torch.empty(f_hi - f_lo, FEAT, device=dev)
+        out_b = torch.empty(b_hi - b_lo, FEAT, device=dev)
+        norm_f, norm_b = norm[f_lo:f_hi], norm[b_lo:b_hi]
+
+        def step(ev=None):
+            exchange_rows(x, pg.fwd_bounds)
+            if ev:
+                ev[0].record()
+            kernels.agg_scaled_sum(pg.fwd.view, x, norm, None, norm_f, out=out_f)
+            if ev:
+                ev[1].record()
+            exchange_rows(gout, pg.bwd_bounds)
+            kernels.agg_scaled_sum(pg.bwd.view, gout, norm, None, norm_b, out=out_b)
+    else:
+        out_f = torch.empty_like(x)
+        out_b = torch.empty_like(x)
+        vf, vb = graph.fwd_view(), graph.bwd_view()
+
+        def step(ev=None):
+            if ev:
+                ev[0].record()
+            kernels.agg_scaled_sum(vf, x, norm, None, norm, out=out_f)
+            if ev:
+                ev[1].record()
+            kernels.agg_scaled_sum(vb, gout, norm, None, norm, out=out_b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = kernels.launch_count
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_beg.record()
+    for i in range(args.steps):
+        step(kev[i])
+    t_end.record()
+    barrier()
+    launches = kernels.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_beg.elapsed_time(t_end)
+    ms_fwd_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_total, ms_fwd_kernel], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_fwd_kernel = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = b_alg_step / (ms_step * 1e-3) / 1e9
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- end to end through the C-ABI host-buffer entry point (pinned host memory) ----
+        xh = x.cpu().pin_memory()
+        gh = gout.cpu().pin_memory()
+        nh = norm.cpu().pin_memory()
+        oh = torch.empty(n, FEAT).pin_memory()
+        oh2 = torch.empty(n, FEAT).pin_memory()
+        scratch = torch.empty(kernels.host_scratch_bytes(n, e, FEAT), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            kernels.agg_scaled_sum_host(vf, xh, oh, scratch, nh, None, nh)
+        torch.cuda.synchronize()
+        k = max(3, min(args.steps, 8))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            kernels.agg_scaled_sum_host(vf, xh, oh, scratch, nh, None, nh)
+            kernels.agg_scaled_sum_host(vb, gh, oh2, scratch, nh, None, nh)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / k * 1e3
+        h2d = 2 * (n * FEAT * 4 + 2 * n * 4)
+        d2h = 2 * n * FEAT * 4
+        extras["e2e"] = {"value": b_alg_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "api": "stg_agg_scaled_sum_f32_host (pinned host buffers, H2D + kernel + D2H per call)"}
+        assert torch.equal(oh, out_f.cpu()), "host-buffer path and device path disagree"
+        del scratch
+        # ---- locality-free variant of the same shape (secondary figure) ----
+        try:
+            d0 = synthetic.products_shaped(seed=0, device=dev, scale=args.scale, locality=0.0)
+            g0 = StaticGraph(torch.stack([d0["src"], d0["dst"]], 1), None, n)
+            nm0 = g0.degree_norm().reshape(-1).contiguous()
+            v0f, v0b = g0.fwd_view(), g0.bwd_view()
+            for _ in range(3):
+                kernels.agg_scaled_sum(v0f, x, nm0, None, nm0, out=out_f)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                kernels.agg_scaled_sum(v0f, x, nm0, None, nm0, out=out_f)
+                kernels.agg_scaled_sum(v0b, gout, nm0, None, nm0, out=out_b)
+            b.record()
+            torch.cuda.synchronize()
+            ms0 = a.elapsed_time(b) / 5
+            extras["locality_free"] = {"ms_per_step": ms0, "value": b_alg_step / (ms0 * 1e-3) / 1e9, "unit": UNIT}
+            del g0, d0
+        except Exception as ex:  # secondary figure only
+            extras["locality_free"] = {"error": str(ex)[:200]}
+        # ---- CPU baseline: the oracle port on the host cores, bounded sample ----
+        t_cpu, e_s, e_f, rows, threads = cpu_reference_sample(d["src"], d["dst"], n, FEAT)
+        cpu_val = b_alg_one * (e_s / e_f) / t_cpu / 1e9
+        extras["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                                  "sample": f"torch-CPU index_add (fp32) forward aggregation of the first {rows} "
+                                            f"destination rows = {e_s} of {e_f} edges, F={FEAT}, best of 3; "
+                                            f"throughput scaled by edge share", "seconds": t_cpu}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = b_alg_one / (ms_fwd_kernel * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config5: GCN aggregation fwd+bwd, ogbn-products-shaped synthetic graph",
+                       "num_nodes": n, "num_edges": e, "feat": FEAT, "locality": args.locality, "window": args.window,
+                       "l2_policy": "inputs (980 MB features + 500 MB structure) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"row-partition x{world} + NCCL row exchange" if world > 1 else "single GPU",
+                       "scale": args.scale},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "kernel": "agg_rows_kernel<4,32,1> (forward, in-edge CSR)",
+                         "kernel_ms": ms_fwd_kernel, "algorithmic_bytes": b_alg_one, "peak_source": peak_src,
+                         "gather_model_gbs": 4.0 * (e * FEAT + n * FEAT + e) / (ms_fwd_kernel * 1e-3) / 1e9},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

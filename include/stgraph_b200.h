@@ -201,6 +201,37 @@ int stg_weighted_row_degree_f32(const StgCsrView* g, const float* edge_weight, f
 int stg_csr_hub_rows(const int32_t* row_offset, int32_t num_nodes, int32_t threshold,
                      int32_t* hub_rows, int32_t capacity, int32_t* hub_count, void* stream);
 
+/* ------------------------------------------------ dynamic-graph snapshots */
+/* A snapshot is the sorted array of its live edge keys (dst<<32 | src), i.e. a packed memory array
+ * without gaps; see csrc/snapshot.cu for why that is the B200 design.  All counts are written to
+ * DEVICE memory (int64) so that nothing synchronises; callers that know the sizes from
+ * preprocessing never read them back. */
+size_t stg_snapshot_workspace_bytes(int64_t max_items);
+
+/* keys_out = sorted, de-duplicated keys of an edge list (dynamic_graph.py:58-63 set()). */
+int stg_snapshot_keys_from_edges(const int32_t* src, const int32_t* dst, int64_t n, int32_t num_nodes,
+                                 uint64_t* keys_out, int64_t* count_out, void* ws, size_t ws_bytes, void* stream);
+
+/* out = a \ b for sorted unique key arrays: the per-timestamp "add" / "delete" lists
+ * (dynamic_graph.py:66-79). */
+int stg_snapshot_diff(const uint64_t* a, int64_t na, const uint64_t* b, int64_t nb, uint64_t* out,
+                      int64_t* count_out, void* ws, size_t ws_bytes, void* stream);
+
+/* out = (keys \ del) U add -- one batched insert/delete step (gpma.cu:1064-1119 edge_update_t /
+ * pcsr.cu:658-717 edge_update_list); swap add/del to revert a timestamp. out needs n + na slots. */
+int stg_snapshot_apply(const uint64_t* keys, int64_t n, const uint64_t* add, int64_t na, const uint64_t* del,
+                       int64_t nd, uint64_t* out, int64_t* count_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Labelled CSR views of a snapshot: forward (rows = dst) and, if bwd_row_offset != NULL, backward
+ * (rows = src, dense transpose carrying the forward labels; gpma.cu:1165-1231, pcsr.cu:794-809).
+ * label = label_base + rank among live keys (1 for PCSR/GPMA, 0 for NaiveGraph).
+ * descending_rows != 0 emits every row back to front (PCSR, pcsr.cu:842-855).
+ * node_ids / degree outputs may be NULL. ws must hold max(n, num_nodes) items. */
+int stg_snapshot_views(const uint64_t* keys, int64_t n, int32_t num_nodes, int32_t descending_rows, int32_t label_base,
+                       int32_t* fwd_row_offset, int32_t* fwd_col, int32_t* fwd_labels, int32_t* fwd_node_ids,
+                       int32_t* bwd_row_offset, int32_t* bwd_col, int32_t* bwd_labels, int32_t* bwd_node_ids,
+                       int32_t* in_degree, int32_t* out_degree, void* ws, size_t ws_bytes, void* stream);
+
 /* D2H copy of an int32 device array -- test hook (csr.cu:172-179 get_array). */
 int stg_get_array_i32(const int32_t* dev_ptr, int64_t count, int32_t* host_out, void* stream);
 

@@ -95,6 +95,15 @@ _SIGNATURES = {
     "stg_degree_norm_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p], True),
     "stg_weighted_row_degree_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p], True),
     "stg_csr_hub_rows": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p], True),
+    "stg_snapshot_workspace_bytes": (c_size_t, [c_int64], False),
+    "stg_snapshot_keys_from_edges": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                                    c_size_t, c_void_p], True),
+    "stg_snapshot_diff": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_void_p], True),
+    "stg_snapshot_apply": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                          c_void_p, c_size_t, c_void_p], True),
+    "stg_snapshot_views": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32] + [c_void_p] * 10
+                           + [c_void_p, c_size_t, c_void_p], True),
     "stg_get_array_i32": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p], True),
 }
 

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
   extern __shared__ float smem[];
   float* regs = smem;                                      // [n_regs][kVmThreads]
   float* accs = smem + prog.n_regs * kVmThreads;           // [n_acc][kVmThreads]
+  float* scratch = accs + prog.n_acc * kVmThreads;         // [kVmThreads] lane-reduction staging
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -52,13 +53,28 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
   const int beg = __ldg(a.g.row_offset + row);
   const int end = __ldg(a.g.row_offset + row + 1);
   const bool seg_pow2 = (dim1 & (dim1 - 1)) == 0 && dim1 <= GROUP;
+  // lanes per chunk: whole dim1-segments only, so a segment never straddles two chunks
+  const int chunk = (dim1 <= GROUP) ? (GROUP / dim1) * dim1 : GROUP;
+  // sum over the dim1 consecutive lanes of this lane's segment, result in every lane of the segment
+  auto segment_sum = [&](float v, int i1) -> float {
+    if (seg_pow2) {
+      for (int o = 1; o < dim1; o <<= 1) v += __shfl_xor_sync(gmask, v, o, GROUP);
+      return v;
+    }
+    scratch[tid] = v;
+    __syncwarp(gmask);
+    float s = 0.f;
+    for (int k = 0; k < dim1; ++k) s += scratch[tid - i1 + k];
+    __syncwarp(gmask);
+    return s;
+  };
 
 #define R(i) regs[(i) * kVmThreads + tid]
 #define ACC(i) accs[(i) * kVmThreads + tid]
 
-  for (int tx0 = 0; tx0 < lanes; tx0 += GROUP) {
+  for (int tx0 = 0; tx0 < lanes; tx0 += chunk) {
     const int tx = tx0 + gl;
-    const bool active = tx < lanes;
+    const bool active = gl < chunk && tx < lanes;
     const int txc = active ? tx : lanes - 1;
     const int i0 = txc / dim1, i1 = txc - i0 * dim1;
     for (int k = 0; k < prog.n_acc; ++k) ACC(k) = prog.acc_init[k];
@@ -98,9 +114,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
         }
         case STG_OP_GSUM: {
           // sum over dim1 inside each dim0 slice (segments of dim1 consecutive lanes), broadcast back
-          float v = active ? R(in.a) : 0.f;
-          for (int o = 1; o < dim1; o <<= 1) v += __shfl_xor_sync(gmask, v, o, GROUP);
-          R(in.dst) = v;
+          R(in.dst) = segment_sum(active ? R(in.a) : 0.f, i1);
           break;
         }
         case STG_OP_STORE: {
@@ -119,10 +133,9 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
             if (active && leader) *dst = v;
           } else if (full) {
             if (active) *dst = v;
-          } else if (t.bc0 && !t.bc1 && seg_pow2) {
-            // [dim0,dim1] -> [dim0,1]: segmented shuffle reduction over dim1 consecutive lanes
-            v = active ? v : 0.f;
-            for (int o = dim1 >> 1; o > 0; o >>= 1) v += __shfl_down_sync(gmask, v, o, GROUP);
+          } else if (t.bc0 && !t.bc1 && dim1 <= GROUP) {
+            // [dim0,dim1] -> [dim0,1]: segmented reduction over dim1 consecutive lanes
+            v = segment_sum(active ? v : 0.f, i1);
             if (active && i1 == 0) *dst = v;
           } else {
             if (active) atomicAdd(dst, v);   // caller zero-fills; generic cross-lane reduction
@@ -153,7 +166,7 @@ template <int GROUP>
 int launch_vm(const VmArgs& a, const StgVmProgram& prog, cudaStream_t stream) {
   const int rows_per_block = (kVmThreads / 32) * (32 / GROUP);
   const int blocks = (a.g.num_nodes + rows_per_block - 1) / rows_per_block;
-  const size_t smem = static_cast<size_t>(prog.n_regs + prog.n_acc) * kVmThreads * sizeof(float);
+  const size_t smem = static_cast<size_t>(prog.n_regs + prog.n_acc + 1) * kVmThreads * sizeof(float);
   vm_kernel<GROUP><<<blocks, kVmThreads, smem, stream>>>(a, prog);
   STG_LAUNCH_CHECK("vm_kernel");
   return STG_OK;
@@ -185,7 +198,7 @@ STG_API int stg_vm_run_f32(const StgCsrView* g, const StgVmProgram* prog, void* 
     }
     if (in.op == STG_OP_GSUM) {
       const int d1 = prog->dim1;
-      STG_CHECK_ARG((d1 & (d1 - 1)) == 0 && d1 <= 32, "GSUM needs dim1 to be a power of two <= 32 (got %d)", d1);
+      STG_CHECK_ARG(d1 <= 32, "GSUM needs dim1 <= 32 (got %d)", d1);
     }
   }
   STG_CHECK_ARG(!needs_eids || g->eids_identity || g->eids || g->num_edges == 0, "eids is NULL");

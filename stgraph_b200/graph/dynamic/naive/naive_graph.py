@@ -1,0 +1,1 @@
+from ..naive_graph import *  # noqa: F401,F403

@@ -1,0 +1,1 @@
+from ..pcsr_graph import *  # noqa: F401,F403
