@@ -80,6 +80,29 @@ int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t feat,
                            const float* nbr_scale, const float* edge_scale,
                            const float* row_scale, float* out, void* stream);
 
+/* Accumulating form: out[r,:] += row_scale[r] * sum(...).  Used when a row's edge set is split in two CSRs
+ * (edges to locally owned sources / edges to halo sources) so that the first pass overlaps the halo
+ * exchange; the passes run in a fixed order, so the result stays deterministic. */
+int stg_agg_scaled_sum_accum_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,
+                                 const float* edge_scale, const float* row_scale, float* out, void* stream);
+
+/* Same operation with the source matrix ROW-PARTITIONED into num_parts blocks (multi-GPU): block q holds
+ * rows [part_bounds[q], part_bounds[q+1]) of x and may live in a peer GPU's memory mapped into this
+ * process (CUDA IPC / symmetric memory): the kernel then fetches remote neighbour rows with NVLink
+ * loads while it aggregates -- the halo exchange is fused into the gather, tile by tile, and no
+ * all-gather is materialised.  g is this rank's row slice of the CSR (global column ids).
+ * x_parts / part_bounds are HOST arrays (num_parts <= STG_MAX_PARTS).  nbr_scale is indexed by global id.
+ * New: the reference is single-GPU. */
+#define STG_MAX_PARTS 16
+int stg_agg_scaled_sum_parts_f32(const StgCsrView* g, const float* const* x_parts, const int32_t* part_bounds,
+                                 int32_t num_parts, int32_t feat, const float* nbr_scale, const float* edge_scale,
+                                 const float* row_scale, float* out, void* stream);
+
+/* Halo pull: out[i,:] = row ids[i] of the row-partitioned matrix (blocks may be peer-GPU memory), i < n_ids.
+ * max_blocks bounds the grid (<= 0: 32) so the copy overlaps a concurrently running aggregation kernel. */
+int stg_halo_pull_f32(const float* const* x_parts, const int32_t* part_bounds, int32_t num_parts, const int64_t* ids,
+                      int64_t n_ids, int32_t feat, float* out, int32_t max_blocks, void* stream);
+
 /* Same operation with HOST buffers: copies x (and the scale vectors) to the
  * device scratch the caller provides, runs the kernel, copies out back.
  * dev_scratch must hold 2*N*feat + 2*N + E floats.  Used for the end-to-end

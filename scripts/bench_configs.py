@@ -1,0 +1,261 @@
+"""Secondary measurements: epoch times of the other BASELINE.json configs (1-4) on one B200.
+
+Not the judged bench line (that is bench.py, config 5); results are written as JSON to
+``gpurun_out/configs.json`` and summarised in ``profiles/``.  Loops follow the reference's benchmark
+scripts: ``benchmarking/gcn/seastar/train.py:78-111`` (config 1),
+``benchmarking/static-temporal-tgcn/seastar/train.py:162-187`` (config 2),
+``benchmarking/gat/seastar/train.py`` shape (config 3), ``benchmarking/dynamic-temporal-tgcn/seastar/train.py:189-231``
+(config 4, reduced decode: MSE on the hidden state instead of link prediction).
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stgraph_b200 import kernels  # noqa: E402
+from stgraph_b200.graph import GPMAGraph, NaiveGraph, PCSRGraph, StaticGraph  # noqa: E402
+from stgraph_b200.nn.pytorch import GATConv, GCNConv, TGCN  # noqa: E402
+from stgraph_b200.utils import synthetic  # noqa: E402
+
+dev = torch.device("cuda")
+out = {}
+
+
+def timed(fn, warm=3, reps=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+# ------------------------------------------------------------------ config 1: 2-layer GCN on Cora shape
+def config1():
+    d = synthetic.cora_shaped(seed=0, device=dev)
+    n = d["num_nodes"]
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, n)
+    g.set_ndata("norm", g.degree_norm())
+    torch.manual_seed(2)
+
+    class GCN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1 = GCNConv(1433, 16, activation=F.relu)
+            self.l2 = GCNConv(16, 7)
+
+        def forward(self, g, x):
+            return self.l2(g, self.l1(g, x))
+
+    model = GCN().to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=5e-4)
+    mask = torch.rand(n, device=dev) < 0.6
+    x, y = d["features"], d["labels"]
+
+    def epoch():
+        logits = model(g, x)
+        loss = F.cross_entropy(logits[mask], y[mask])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    l0 = kernels.launch_count
+    ms = timed(epoch, warm=3, reps=50)
+    out["config1_gcn_cora_epoch_ms"] = ms
+    out["config1_our_kernel_launches_per_epoch"] = (kernels.launch_count - l0) / 53
+
+
+# ------------------------------------------------------------------ config 2: static-temporal TGCN
+class STGraphTGCN(torch.nn.Module):
+    def __init__(self, node_features, hidden, out_features, fused):
+        super().__init__()
+        self.temporal = TGCN(node_features, hidden, fused=fused)
+        self.linear = torch.nn.Linear(hidden, node_features)
+        self.linear2 = torch.nn.Linear(node_features, out_features)
+
+    def forward(self, g, x, w, h):
+        h = self.temporal(g, x, w, h)
+        y = self.linear(F.relu(h))
+        return self.linear2(y), y, h
+
+
+def config2():
+    d = synthetic.wikimaths_shaped(seed=0, device=dev)
+    n, lags, T = d["num_nodes"], d["lags"], d["num_timestamps"]
+    steps = T - lags                       # 723 (tests/scripts/v1_1_0/.../tgcn/train.py:145)
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, n)
+    g.set_ndata("norm", g.degree_norm())
+    # edge weights must be in (dst,src) = eid order (trap T8); the generator's order is arbitrary, any fixed order works
+    w = d["edge_weight"].reshape(-1, 1).contiguous()
+    targets = d["targets"]
+    res = {}
+    for name, fused in (("dropin", False), ("fused", True)):
+        torch.manual_seed(0)
+        model = STGraphTGCN(lags, 16, 1, fused).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+
+        def epoch():
+            opt.zero_grad()
+            cost, h = 0, None
+            y_hat = torch.randn(n, lags, device=dev)
+            for t in range(steps):
+                y_out, y_hat, h = model(g, y_hat, w, h)
+                cost = cost + torch.mean((y_out.reshape(-1) - targets[t]) ** 2)
+            cost = cost / (steps + 1)
+            cost.backward()
+            opt.step()
+
+        l0 = kernels.launch_count
+        res[name] = timed(epoch, warm=1, reps=3)
+        res[name + "_launches"] = (kernels.launch_count - l0) / 4
+    # fused cell + the whole epoch (723 steps fwd + bwd + Adam) captured in ONE CUDA graph
+    torch.manual_seed(0)
+    model = STGraphTGCN(lags, 16, 1, True).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True)
+    y0 = torch.randn(n, lags, device=dev)
+
+    def epoch_body():
+        opt.zero_grad(set_to_none=False)
+        cost, h, y_hat = 0, None, y0
+        for t in range(steps):
+            y_out, y_hat, h = model(g, y_hat, w, h)
+            cost = cost + torch.mean((y_out.reshape(-1) - targets[t]) ** 2)
+        cost = cost / (steps + 1)
+        cost.backward()
+        opt.step()
+        return cost
+
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                epoch_body()
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            cost = epoch_body()
+        res["fused_cudagraph"] = timed(graph.replay, warm=1, reps=5)
+        res["fused_cudagraph_loss"] = float(cost)
+    except Exception as ex:      # report, do not hide
+        res["fused_cudagraph_error"] = repr(ex)[:300]
+    out["config2_tgcn_wikimaths_epoch_ms"] = res
+    out["config2_steps_per_epoch"] = steps
+
+
+# ------------------------------------------------------------------ config 3: GAT fwd+bwd on arxiv shape
+def config3():
+    d = synthetic.arxiv_shaped(seed=0, device=dev)
+    n = d["num_nodes"]
+    e = int(d["src"].shape[0])
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, n)
+    x = torch.randn(n, 128, device=dev)
+    gout = torch.randn(n, 8, 16, device=dev)
+    res = {"num_nodes": n, "num_edges": e, "max_in_degree": int(g.in_degrees_tensor().max())}
+    for name, mode in (("stock_vm", "stock"), ("fused_softmax", "fused")):
+        torch.manual_seed(0)
+        layer = GATConv(128, 16, 8, softmax=mode).to(dev)
+
+        def step():
+            layer.zero_grad()
+            y = layer(g, x)
+            y.backward(gout)
+
+        res[name + "_fwd_bwd_ms"] = timed(step, warm=3, reps=10)
+    # kernel-only figures of the fused path against its algorithmic bytes
+    from stgraph_b200.ops_gat import gat_edge_softmax_aggregate
+    feat = torch.randn(n, 8, 16, device=dev, requires_grad=True)
+    el = torch.randn(n, 8, 1, device=dev, requires_grad=True)
+    er = torch.randn(n, 8, 1, device=dev, requires_grad=True)
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    fw, bw = [], []
+    for i in range(8):
+        a.record()
+        y = gat_edge_softmax_aggregate(g, el, er, feat)
+        b.record()
+        y.backward(gout)
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            fw.append(a.elapsed_time(b))
+            bw.append(b.elapsed_time(c))
+    hd = 128
+    b_fwd = 4 * (2 * n * hd + 4 * n * 8 + e + n + 1)
+    b_bwd = 4 * (4 * n * hd + 6 * n * 8 + 2 * (e + n + 1))
+    res["fused_fwd_kernel_ms"] = sum(fw) / len(fw)
+    res["fused_bwd_kernels_ms"] = sum(bw) / len(bw)
+    res["fused_fwd_alg_gbs"] = b_fwd / (res["fused_fwd_kernel_ms"] * 1e-3) / 1e9
+    res["fused_bwd_alg_gbs"] = b_bwd / (res["fused_bwd_kernels_ms"] * 1e-3) / 1e9
+    out["config3_gat_arxiv"] = res
+
+
+# ------------------------------------------------------------------ config 4: dynamic TGCN on GPMAGraph
+def config4(scale=1.0):
+    n = int(1_000_000 * scale)
+    base, slide, T = int(10_000_000 * scale), int(100_000 * scale), 100
+    src, dst = synthetic.temporal_stream(n, base + slide * (T - 1) + 1000, alpha=1.8, seed=0, device=dev)
+    snaps = synthetic.sliding_window_snapshots(src, dst, base, slide, T)
+    snaps = [torch.stack([s, d_], 1) for s, d_ in snaps]
+    res = {"num_nodes": n, "snapshots": len(snaps)}
+    t0 = time.perf_counter()
+    G = GPMAGraph(snaps, n)
+    torch.cuda.synchronize()
+    res["gpma_construct_s"] = time.perf_counter() - t0
+    res["edges_t0"] = G.get_num_edges()
+    res["adds_per_step"] = int(G.graph_updates["1"]["add"].shape[0])
+    res["deletes_per_step"] = int(G.graph_updates["1"]["delete"].shape[0])
+    # structure update cost per snapshot (apply + forward view + hub schedule), device time
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    G.reset_graph()
+    a.record()
+    for t in range(1, len(snaps)):
+        G.get_graph(t)
+    b.record()
+    torch.cuda.synchronize()
+    res["gpma_update_ms_per_snapshot"] = a.elapsed_time(b) / (len(snaps) - 1)
+    u = res["adds_per_step"] + res["deletes_per_step"]
+    res["gpma_update_alg_bytes"] = 12 * u + 12 * res["edges_t0"] + 8 * n
+    # TGCN(32, 64) over the snapshots, backprop every 20 (dynamic-temporal-tgcn/seastar/train.py:189-231)
+    torch.manual_seed(0)
+    model = TGCN(32, 64, fused=True).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    x = torch.randn(n, 32, device=dev)
+
+    def epoch(graph):
+        graph.reset_graph()
+        h = None
+        cost = 0
+        for t in range(len(snaps)):
+            graph.get_graph(t)
+            graph.set_ndata("norm", graph.degree_norm())
+            h = model(graph, x, None, h)
+            cost = cost + (h ** 2).mean()
+            if (t + 1) % 20 == 0:
+                opt.zero_grad()
+                cost.backward()
+                opt.step()
+                h, cost = h.detach(), 0
+
+    res["tgcn_gpma_epoch_ms"] = timed(lambda: epoch(G), warm=1, reps=2)
+    out["config4_dynamic_tgcn"] = res
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["1", "2", "3", "4"]
+    for w in which:
+        try:
+            {"1": config1, "2": config2, "3": config3, "4": config4}[w]()
+        except Exception as ex:
+            import traceback
+            traceback.print_exc()
+            out[f"config{w}_error"] = repr(ex)[:400]
+        torch.cuda.empty_cache()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
+    print(json.dumps(out, indent=1))

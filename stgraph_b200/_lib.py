@@ -81,6 +81,12 @@ _SIGNATURES = {
     "stg_device_info": (ctypes.c_int, [ctypes.c_int, _P(c_int32), _P(c_int64), _P(c_int32), _P(c_int32)], True),
     "stg_agg_scaled_sum_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p], True),
+    "stg_agg_scaled_sum_accum_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                                    c_void_p, c_void_p], True),
+    "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,
+                                                    c_void_p, c_void_p, c_void_p, c_void_p], True),
+    "stg_halo_pull_f32": (ctypes.c_int, [_P(c_void_p), _P(c_int32), c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32,
+                                         c_void_p], True),
     "stg_agg_scaled_sum_f32_host": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                                    c_void_p, c_void_p, c_size_t, c_void_p], True),
     "stg_gat_softmax_fwd_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_int32, c_int32,

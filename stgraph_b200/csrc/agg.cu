@@ -58,7 +58,22 @@ struct AggParams {
   const float* __restrict__ ns;
   const float* __restrict__ es;
   const float* __restrict__ rs;
+  // Row-partitioned source matrix (multi-GPU): block q holds rows [bounds[q], bounds[q+1]) and may
+  // live in a PEER GPU's memory (NVLink loads); nparts == 0 means one local matrix `x`.
+  int accumulate;     // 1: out += result (second pass over a split edge set), 0: out = result
+  int nparts;
+  int bounds[STG_MAX_PARTS + 1];
+  const float* xs[STG_MAX_PARTS];
 };
+
+// Address of source row c: local matrix, or the owner's block when the matrix is partitioned.
+__device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
+  if (p.nparts == 0) return p.x + static_cast<size_t>(c) * p.ld;
+  int o = 0;
+#pragma unroll
+  for (int q = 1; q < STG_MAX_PARTS; ++q) o += (q < p.nparts && c >= p.bounds[q]) ? 1 : 0;
+  return p.xs[o] + static_cast<size_t>(c - p.bounds[o]) * p.ld;
+}
 
 // Accumulate edges [beg,end) visited with stride `step` batches of GROUP edges,
 // starting at batch `first`.  All lanes of a group execute this together.
@@ -110,7 +125,7 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const float* src = p.x + static_cast<size_t>(c[u]) * p.ld;
+        const float* src = src_row(p, c[u]);
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
           if (act[k] && (j + u) < n) v[u][k] = ld_row<VEC>(src + off[k]);
@@ -154,6 +169,7 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
     const int o = (gl + k * GROUP) * VEC;
     if (o < p.width) {
       scale_vec(acc[k], r);
+      if (p.accumulate) add_vec(acc[k], *reinterpret_cast<const T*>(dst + o));
       st_row<VEC>(dst + o, acc[k]);
     }
   }
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p)
         const int o = (lane + k * GROUP) * VEC;
         if (o < p.width) {
           scale_vec(sum, r);
+          if (p.accumulate) add_vec(sum, *reinterpret_cast<const T*>(dst + o));
           st_row<VEC>(dst + o, sum);
         }
       }
@@ -257,8 +274,14 @@ int dispatch_group(const AggParams& p, cudaStream_t stream) {
 }  // namespace
 
 int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, const float* ns,
-                          const float* es, const float* rs, float* out, cudaStream_t stream) {
+                          const float* es, const float* rs, float* out, cudaStream_t stream,
+                          int nparts = 0, const float* const* parts = nullptr, const int32_t* bounds = nullptr,
+                          int accumulate = 0) {
   AggParams p;
+  p.accumulate = accumulate;
+  p.nparts = nparts;
+  for (int q = 0; q < STG_MAX_PARTS; ++q) p.xs[q] = q < nparts ? parts[q] : nullptr;
+  for (int q = 0; q <= STG_MAX_PARTS; ++q) p.bounds[q] = (nparts > 0 && q <= nparts) ? bounds[q] : 0;
   p.row_off = g->row_offset;
   p.col = g->column_indices;
   p.eids = g->eids;
@@ -273,12 +296,22 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   p.ns = ns;
   p.es = es;
   p.rs = rs;
+  bool al16 = aligned16(out), al8 = aligned8(out);
+  if (nparts == 0) {
+    al16 = al16 && aligned16(x);
+    al8 = al8 && aligned8(x);
+  }
+  for (int q = 0; q < nparts; ++q) {
+    al16 = al16 && aligned16(parts[q]);
+    al8 = al8 && aligned8(parts[q]);
+  }
   int vec = 1;
-  if (feat % 4 == 0 && aligned16(x) && aligned16(out)) vec = 4;
-  else if (feat % 2 == 0 && aligned8(x) && aligned8(out)) vec = 2;
+  if (feat % 4 == 0 && al16) vec = 4;
+  else if (feat % 2 == 0 && al8) vec = 2;
   const int chunk = 32 * 4 * vec;  // widest tile one launch covers
   for (int f0 = 0; f0 < feat; f0 += chunk) {
-    p.x = x + f0;
+    p.x = x ? x + f0 : nullptr;
+    for (int q = 0; q < nparts; ++q) p.xs[q] = parts[q] + f0;
     p.out = out + f0;
     p.width = min(chunk, feat - f0);
     int rc;
@@ -349,4 +382,34 @@ STG_API int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host
   STG_CUDA(cudaMemcpyAsync(out_host, dout, n * feat * sizeof(float), cudaMemcpyDeviceToHost, s));
   STG_CUDA(cudaStreamSynchronize(s));
   return STG_OK;
+}
+
+STG_API int stg_agg_scaled_sum_parts_f32(const StgCsrView* g, const float* const* x_parts, const int32_t* part_bounds,
+                                         int32_t num_parts, int32_t feat, const float* nbr_scale,
+                                         const float* edge_scale, const float* row_scale, float* out, void* stream) {
+  int rc = validate_view(g, edge_scale != nullptr);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  STG_CHECK_ARG(num_parts >= 1 && num_parts <= STG_MAX_PARTS, "num_parts must be in [1, %d] (got %d)", STG_MAX_PARTS,
+                num_parts);
+  STG_CHECK_ARG(x_parts && part_bounds && out, "NULL argument");
+  for (int q = 0; q < num_parts; ++q) {
+    STG_CHECK_ARG(part_bounds[q] <= part_bounds[q + 1], "part_bounds must be non-decreasing");
+    STG_CHECK_ARG(x_parts[q] != nullptr || part_bounds[q] == part_bounds[q + 1], "x_parts[%d] is NULL", q);
+  }
+  STG_CHECK_ARG(part_bounds[0] == 0, "part_bounds[0] must be 0");
+  if (g->num_nodes == 0) return STG_OK;
+  return agg_scaled_sum_device(g, nullptr, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream), num_parts,
+                               x_parts, part_bounds);
+}
+
+STG_API int stg_agg_scaled_sum_accum_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,
+                                         const float* edge_scale, const float* row_scale, float* out, void* stream) {
+  int rc = validate_view(g, edge_scale != nullptr);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
+  STG_CHECK_ARG(x != out, "x and out must not alias");
+  return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream), 0, nullptr, nullptr, 1);
 }

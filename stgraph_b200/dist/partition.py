@@ -75,6 +75,20 @@ class PartitionedGraph:
         self.fwd = _LocalSlice(graph._forward_graph, self.fwd_bounds[rank], self.fwd_bounds[rank + 1])
         self.bwd = _LocalSlice(graph._backward_graph, self.bwd_bounds[rank], self.bwd_bounds[rank + 1])
 
+    def halo_plans(self, group=None):
+        """Halo-only exchange plans: (forward, backward).
+
+        Feature rows are owned by the forward (destination) partition -- layer outputs are produced
+        there -- and gradient rows likewise; the backward aggregation computes the source rows of
+        ``bwd_bounds`` and fetches the gradient rows it needs from their forward owners.
+        """
+        from .halo import HaloPlan
+
+        g = self.graph
+        fwd = HaloPlan(g._forward_graph, self.fwd_bounds, self.fwd_bounds, self.rank, self.world, group)
+        bwd = HaloPlan(g._backward_graph, self.bwd_bounds, self.fwd_bounds, self.rank, self.world, group)
+        return fwd, bwd
+
     def local_rows(self, direction: str):
         b = self.fwd_bounds if direction == "fwd" else self.bwd_bounds
         return b[self.rank], b[self.rank + 1]

@@ -28,31 +28,38 @@ def _check(t: torch.Tensor, name: str, dtype=torch.float32):
 
 
 def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
-                   out: torch.Tensor | None = None) -> torch.Tensor:
+                   out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
     """``out[r] = row_scale[r] * sum_e nbr_scale[c_e] * edge_scale[eid_e] * x[c_e]`` (see ``stg_agg_scaled_sum_f32``)."""
     global launch_count
     _check(x, "x")
-    n = view.num_nodes
-    if x.shape[0] != n:
-        raise ValueError(f"x has {x.shape[0]} rows for a graph of {n} nodes")
-    feat = x.numel() // max(n, 1) if n > 0 else 0
-    for nm, t, cnt in (("nbr_scale", nbr_scale, n), ("row_scale", row_scale, n), ("edge_scale", edge_scale, None)):
+    n = view.num_nodes                      # rows of this view (a row slice of a partitioned graph has fewer rows than x)
+    if x.dim() < 2:
+        raise ValueError("x must be [rows, feat...]")
+    feat = x.numel() // max(x.shape[0], 1)
+    for nm, t in (("nbr_scale", nbr_scale), ("edge_scale", edge_scale)):
         if t is not None:
             _check(t, nm)
-            if cnt is not None and t.numel() != cnt:
-                raise ValueError(f"{nm} must have {cnt} elements, got {t.numel()}")
+    if nbr_scale is not None and nbr_scale.numel() != x.shape[0]:
+        raise ValueError(f"nbr_scale must have one entry per row of x ({x.shape[0]}), got {nbr_scale.numel()}")
+    if row_scale is not None:
+        _check(row_scale, "row_scale")
+        if row_scale.numel() != n:
+            raise ValueError(f"row_scale must have {n} elements, got {row_scale.numel()}")
     if edge_scale is not None and edge_scale.numel() < view.num_edges:
         raise ValueError(f"edge_scale has {edge_scale.numel()} elements for {view.num_edges} edges")
     if out is None:
+        if x.shape[0] != n:
+            raise ValueError(f"x has {x.shape[0]} rows for a view of {n} rows: pass out= for a row slice")
         out = torch.empty_like(x)
     else:
         _check(out, "out")
-        if out.shape != x.shape:
-            raise ValueError("out must have the shape of x")
+        if out.shape[0] != n or out.numel() != n * feat:
+            raise ValueError(f"out must be [{n}, {feat}], got {tuple(out.shape)}")
     if n == 0 or feat == 0:
         return out
-    _lib.call("stg_agg_scaled_sum_f32", ctypes.byref(view), x.data_ptr(), feat, _lib.ptr(nbr_scale),
-              _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(), _lib.current_stream_ptr())
+    _lib.call("stg_agg_scaled_sum_accum_f32" if accumulate else "stg_agg_scaled_sum_f32", ctypes.byref(view),
+              x.data_ptr(), feat, _lib.ptr(nbr_scale), _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(),
+              _lib.current_stream_ptr())
     launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
     return out
 
@@ -83,3 +90,22 @@ def device_info(device: int = 0):
     mnr = ctypes.c_int32()
     _lib.call("stg_device_info", device, ctypes.byref(sm), ctypes.byref(l2), ctypes.byref(maj), ctypes.byref(mnr))
     return {"sm_count": sm.value, "l2_bytes": l2.value, "cc": (maj.value, mnr.value)}
+
+
+def agg_scaled_sum_parts(view: _lib.StgCsrView, part_ptrs, part_bounds, feat: int, nbr_scale=None, edge_scale=None,
+                         row_scale=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Aggregation whose source matrix is row-partitioned over ``len(part_ptrs)`` blocks (possibly peer-GPU memory).
+
+    ``part_ptrs``: raw device addresses of the blocks, ``part_bounds``: ``P+1`` global row boundaries.
+    See ``stg_agg_scaled_sum_parts_f32``.
+    """
+    global launch_count
+    p = len(part_ptrs)
+    assert len(part_bounds) == p + 1
+    _check(out, "out")
+    ptrs = (ctypes.c_void_p * p)(*[ctypes.c_void_p(int(a)) for a in part_ptrs])
+    bounds = (ctypes.c_int32 * (p + 1))(*[int(b) for b in part_bounds])
+    _lib.call("stg_agg_scaled_sum_parts_f32", ctypes.byref(view), ptrs, bounds, p, int(feat), _lib.ptr(nbr_scale),
+              _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(), _lib.current_stream_ptr())
+    launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
+    return out

@@ -1,0 +1,43 @@
+"""GCN aggregation as a direct torch autograd op (no tracing, no executor): the temporal-loop fast path.
+
+``out = norm * sum_{u in in(v)} norm[u] * w[eid] * h[u]`` forward on the in-edge CSR, the adjoint
+on the out-edge CSR -- the same two launches the compiler produces for ``GCNConv``'s vertex program
+(``stgraph/nn/pytorch/static/gcn_conv.py:162-182``), minus the per-call Python of the executor
+(~25 tiny kernels + 3 executor round trips per TGCN step dominate configs 1-2).
+Sync-free and allocation-free on the C side, so a whole BPTT window can be captured in a CUDA graph.
+For dynamic graphs the snapshot's views are captured at forward time (they are immutable tensors), so
+no rewind is needed in backward.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels
+
+
+class _GcnAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fwd_view, bwd_view, keepalive, h, norm, edge_weight):
+        h = h.contiguous()
+        nflat = norm.reshape(-1)
+        wflat = edge_weight.reshape(-1) if edge_weight is not None else None
+        out = kernels.agg_scaled_sum(fwd_view, h, nflat, wflat, nflat)
+        ctx.bwd_view, ctx.keepalive = bwd_view, keepalive
+        ctx.save_for_backward(nflat, wflat if wflat is not None else nflat)
+        ctx.weighted = wflat is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        nflat, wflat = ctx.saved_tensors
+        gh = kernels.agg_scaled_sum(ctx.bwd_view, gout.contiguous(), nflat, wflat if ctx.weighted else None, nflat)
+        return None, None, None, gh, None, None
+
+
+def gcn_aggregate(graph, h, norm, edge_weight=None):
+    """Differentiable w.r.t. ``h`` only (like the reference: no gradient for ``norm`` / ``edge_weight``)."""
+    if not h.is_cuda:
+        raise RuntimeError("h must live on a CUDA device (stgraph_b200 has no CPU path)")
+    fwd, bwd = graph.fwd_view(), graph.bwd_view()
+    keep = (graph._forward_graph, graph._backward_graph)
+    return _GcnAggregate.apply(fwd, bwd, keep, h, norm, edge_weight)

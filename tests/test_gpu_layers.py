@@ -287,3 +287,30 @@ def test_fused_edge_softmax_rejects_unsupported_dim(cuda):
     feat = torch.randn(50, 2, 6, device=cuda)          # 6 lanes per head: not a power of two
     with pytest.raises(RuntimeError, match="power of two"):
         gat_edge_softmax_aggregate(g, el, el, feat)
+
+
+def test_tgcn_fused_cell_equals_reference_structure(cuda):
+    """fused=True (one GEMM + one aggregation of width 3H) gives the same values and gradients."""
+    from stgraph_b200.nn.pytorch import TGCN
+
+    n, e = 300, 3500
+    g, src, dst = _graph(n, e, 13, cuda)
+    g.set_ndata("norm", g.degree_norm())
+    torch.manual_seed(7)
+    a = TGCN(8, 16).to(cuda)
+    b = TGCN(8, 16, fused=True).to(cuda)
+    b.load_state_dict(a.state_dict())
+    w = torch.rand(e, 1, device=cuda) + 0.1
+    xs = [torch.randn(n, 8, device=cuda) for _ in range(5)]
+    outs = []
+    for cell in (a, b):
+        H, cost = None, 0
+        for x in xs:
+            H = cell(g, x, w, H)
+            cost = cost + (H ** 2).mean()
+        cost.backward()
+        outs.append((H.detach(), {k: p.grad.detach().clone() for k, p in cell.named_parameters()}))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6)
+    for k in outs[0][1]:
+        ga, gb = outs[0][1][k], outs[1][1][k]
+        assert (ga - gb).abs().max() <= 1e-5 * ga.abs().max() + 1e-7, k
