@@ -164,8 +164,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config5 ogbn-products-shaped GCN aggregation F=100, CPU sample",
-                       "sample_edges": e_s, "sample_rows": rows},
+            "config": {"workload": "config5: GCN aggregation fwd+bwd, ogbn-products-shaped synthetic graph",
+                       "num_nodes": n_full, "num_edges": e_full, "feat": FEAT, "locality": args.locality,
+                       "window": args.window, "scale": args.scale,
+                       "sample": {"edges": e_s, "rows": rows, "graph_nodes": n,
+                                  "note": "each step = forward aggregation of a bounded row sample; value scaled by edge share"}},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"forward aggregation of the first {rows} destination rows ({e_s} edges, F={FEAT}) "
                                        f"of a {n}-node graph from the same generator; throughput scaled by edge share"},
@@ -207,7 +210,7 @@ def main():
 
     halo_info = None
     parity = None
-    dist_mode = os.environ.get("STG_DIST_MODE", "pull")
+    dist_mode = os.environ.get("STG_DIST_MODE", "push")
     if world > 1:
         pg = PartitionedGraph(graph, rank, world)
         # single-GPU result of this rank's rows, to check the partitioned path after the first step
@@ -226,7 +229,42 @@ def main():
             except Exception as ex:            # symmetric memory unavailable: fall back to the NCCL halo exchange
                 if rank == 0:
                     print(f"[bench] peer-memory path unavailable ({ex!r}); using NCCL halo all-to-all", file=sys.stderr)
-        if peer_ok and dist_mode == "pull":
+        if dist_mode == "push":
+            try:
+                hf, hb = pg.halo_plans()
+                hf.setup_push(FEAT)
+                hb.setup_push(FEAT)
+                peer_ok = True
+            except Exception as ex:
+                peer_ok = False
+                if rank == 0:
+                    print(f"[bench] peer-memory push path unavailable ({ex!r}); using NCCL halo all-to-all", file=sys.stderr)
+        if peer_ok and dist_mode == "push":
+            own_lo, own_hi = hf.own_lo, hf.own_hi
+            x_own = x[own_lo:own_hi].clone()
+            g_own = gout[own_lo:own_hi].clone()
+            ns_own = norm[own_lo:own_hi].contiguous()
+            nsh_f, nsh_b = norm[hf.halo_ids].contiguous(), norm[hb.halo_ids].contiguous()   # norm is replicated (10 MB)
+            rs_f = norm[hf.row_lo:hf.row_hi].contiguous()
+            rs_b = norm[hb.row_lo:hb.row_hi].contiguous()
+            out_f = torch.empty(hf.n_rows, FEAT, device=dev)
+            out_b = torch.empty(hb.n_rows, FEAT, device=dev)
+            push_blocks = int(os.environ.get("STG_PUSH_BLOCKS", "32"))
+            halo_info = {"mode": "halo rows pushed over NVLink by our kernel (posted stores into symmetric memory), "
+                                 "halo pass concurrent with the own-source pass (vector red.add); no NCCL on the data path",
+                         "halo_rows_fwd": hf.n_halo, "halo_rows_bwd": hb.n_halo, "own_rows": hf.n_own,
+                         "full_allgather_rows": n - hf.n_own, "halo_edges_fwd": int(hf.halo_cols.shape[0]),
+                         "own_edges_fwd": int(hf.own_cols.shape[0]), "push_blocks": push_blocks}
+            del x, gout
+
+            def step(ev=None):
+                if ev:
+                    ev[0].record()
+                hf.aggregate_push(kernels, x_own, ns_own, nsh_f, rs_f, out_f, push_blocks=push_blocks)
+                if ev:
+                    ev[1].record()
+                hb.aggregate_push(kernels, g_own, ns_own, nsh_b, rs_b, out_b, push_blocks=push_blocks)
+        elif peer_ok and dist_mode == "pull":
             hf, hb = pg.halo_plans()
             own_lo, own_hi = hf.own_lo, hf.own_hi
             px.own.copy_(x[own_lo:own_hi])
@@ -241,7 +279,7 @@ def main():
             out_b = torch.empty(hb.n_rows, FEAT, device=dev)
             hf.split_views()
             hb.split_views()
-            pull_blocks = int(os.environ.get("STG_PULL_BLOCKS", "32"))
+            pull_blocks = int(os.environ.get("STG_PULL_BLOCKS", "64"))
             halo_info = {"mode": "halo rows pulled over NVLink by our kernel (symmetric memory), overlapped with the "
                                  "own-source pass; no NCCL on the data path",
                          "halo_rows_fwd": hf.n_halo, "halo_rows_bwd": hb.n_halo, "own_rows": hf.n_own,
@@ -328,6 +366,20 @@ def main():
     barrier()
     launches = kernels.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1 and os.environ.get("STG_DIST_PROFILE") and dist_mode == "pull":
+        hf.profile = []
+        for _ in range(5):
+            hf.aggregate_pull(kernels, px, halo_f, ns_own, nsh_f, rs_f, out_f, pull_blocks=pull_blocks)
+        summ = hf.profile_summary()
+        summ.update({"rows": hf.n_rows, "own_edges": int(hf.own_cols.shape[0]), "halo_edges": int(hf.halo_cols.shape[0]),
+                     "halo_rows": hf.n_halo})
+        hf.profile = None
+        allsum = [None] * world
+        dist.all_gather_object(allsum, summ)
+        if rank == 0:
+            for r_, s_ in enumerate(allsum):
+                print(f"[bench] rank {r_} aggregate_pull segments (ms): " + json.dumps({k: round(v, 3) for k, v in s_.items()}),
+                      file=sys.stderr)
     ms_total = t_beg.elapsed_time(t_end)
     ms_fwd_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     if world > 1:

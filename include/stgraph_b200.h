@@ -86,6 +86,13 @@ int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t feat,
 int stg_agg_scaled_sum_accum_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,
                                  const float* edge_scale, const float* row_scale, float* out, void* stream);
 
+/* Reducing form: out[r,:] += ... issued as red.global.add (vector atomics, no read round trip); rows without
+ * edges are not touched.  Lets the two passes over a split edge set run CONCURRENTLY on two streams into a
+ * zero-filled buffer: every element then receives at most two addends, and 0 + a + b == 0 + b + a exactly,
+ * so the result is independent of the interleaving (deterministic). */
+int stg_agg_scaled_sum_red_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,
+                               const float* edge_scale, const float* row_scale, float* out, void* stream);
+
 /* Same operation with the source matrix ROW-PARTITIONED into num_parts blocks (multi-GPU): block q holds
  * rows [part_bounds[q], part_bounds[q+1]) of x and may live in a peer GPU's memory mapped into this
  * process (CUDA IPC / symmetric memory): the kernel then fetches remote neighbour rows with NVLink
@@ -102,6 +109,13 @@ int stg_agg_scaled_sum_parts_f32(const StgCsrView* g, const float* const* x_part
  * max_blocks bounds the grid (<= 0: 32) so the copy overlaps a concurrently running aggregation kernel. */
 int stg_halo_pull_f32(const float* const* x_parts, const int32_t* part_bounds, int32_t num_parts, const int64_t* ids,
                       int64_t n_ids, int32_t feat, float* out, int32_t max_blocks, void* stream);
+
+/* Halo push: the owner writes local row send_rows[j] to row send_slot[j] of peer send_peer[j]'s halo buffer
+ * (peer_halo[q] = base address of rank q's buffer mapped into this process).  NVLink stores are posted,
+ * so a small grid reaches link rate while the aggregation kernel runs on the other SMs. */
+int stg_halo_push_f32(const float* own, int32_t feat, const int64_t* send_rows, const int32_t* send_peer,
+                      const int64_t* send_slot, int64_t n_items, float* const* peer_halo, int32_t num_parts,
+                      int32_t max_blocks, void* stream);
 
 /* Same operation with HOST buffers: copies x (and the scale vectors) to the
  * device scratch the caller provides, runs the kernel, copies out back.

@@ -83,6 +83,10 @@ _SIGNATURES = {
                                               c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_accum_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                                     c_void_p, c_void_p], True),
+    "stg_agg_scaled_sum_red_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p], True),
+    "stg_halo_push_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, _P(c_void_p), c_int32,
+                                         c_int32, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,
                                                     c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_halo_pull_f32": (ctypes.c_int, [_P(c_void_p), _P(c_int32), c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32,

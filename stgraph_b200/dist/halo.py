@@ -94,7 +94,7 @@ class HaloPlan:
         v.eids = eids.data_ptr() if n_e else None
         v.node_ids = None
         v.num_nodes = self.n_rows
-        v.num_edges = self.num_global_edges
+        v.num_edges = n_e                  # edges of THIS sub-CSR (the kernel picks its row geometry from the mean degree)
         v.eid_base = self.eid_base
         v.eids_identity = 0
         v.hub_rows = hub_rows.data_ptr() if has_hubs else None
@@ -152,19 +152,111 @@ class HaloPlan:
             self._pull_bounds = (ctypes.c_int32 * (p + 1))(*peer.bounds)
         v_own, v_halo = self.split_views()
         cur = torch.cuda.current_stream()
+        prof = getattr(self, "profile", None)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)] if prof is not None else None
+        if ev:
+            ev[0].record(cur)
         peer.barrier()                                   # every rank's block is written
+        if ev:
+            ev[1].record(cur)
         if self.n_halo > 0:
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
+                if ev:
+                    ev[6].record(self._side)
                 _lib.call("stg_halo_pull_f32", self._pull_ptrs, self._pull_bounds, len(peer.ptrs), self.halo_ids.data_ptr(),
                           self.n_halo, int(halo_buf.shape[1]), halo_buf.data_ptr(), int(pull_blocks),
                           self._side.cuda_stream)
+                if ev:
+                    ev[7].record(self._side)
         kernels.agg_scaled_sum(v_own, peer.own, ns_own, es, rs, out=out)
+        if ev:
+            ev[2].record(cur)
         if self.n_halo > 0:
             cur.wait_stream(self._side)
+            if ev:
+                ev[3].record(cur)
             kernels.agg_scaled_sum(v_halo, halo_buf, ns_halo, es, rs, out=out, accumulate=True)
+        if ev:
+            ev[4].record(cur)
         peer.barrier()                                   # nobody still reads my block when I overwrite it next
+        if ev:
+            ev[5].record(cur)
+            prof.append(ev)
         return out
+
+    # ------------------------------------------------- push form (posted NVLink stores, fully overlapped)
+    def setup_push(self, feat: int):
+        """Symmetric double-buffered halo storage + the (row, peer, slot) send list for ``stg_halo_push_f32``."""
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dev = self.local_row_offset.device
+        group = self.group if self.group is not None else dist.group.WORLD
+        mx = torch.tensor([self.n_halo], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        self._max_halo = max(int(mx.item()), 1)
+        self._halo_symm = symm_mem.empty((2 * self._max_halo, feat), dtype=torch.float32, device=dev)
+        self._halo_hdl = symm_mem.rendezvous(self._halo_symm, group)
+        base = [int(a) for a in self._halo_hdl.buffer_ptrs]
+        stride = self._max_halo * feat * 4
+        self._push_ptrs = [(ctypes.c_void_p * self.world)(*[ctypes.c_void_p(b + k * stride) for b in base]) for k in (0, 1)]
+        # where my rows land in each requester's halo buffer: requesters order their halo by owner, then id
+        recv_off = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        recv_off[1:] = torch.cumsum(torch.as_tensor(self.out_splits[:-1], dtype=torch.int64, device=dev), 0)
+        dst_off = torch.empty_like(recv_off)
+        dist.all_to_all_single(dst_off, recv_off, group=self.group)
+        counts = torch.as_tensor(self.in_splits, dtype=torch.int64, device=dev)
+        peer = torch.repeat_interleave(torch.arange(self.world, device=dev, dtype=torch.int64), counts)
+        seg_start = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        seg_start[1:] = torch.cumsum(counts[:-1], 0)
+        within = torch.arange(int(counts.sum()), device=dev, dtype=torch.int64) - seg_start[peer]
+        self._send_peer = peer.to(torch.int32).contiguous()
+        self._send_slot = (dst_off[peer] + within).contiguous()
+        self._side = torch.cuda.Stream(priority=-1)
+        self._iter = 0
+        self._feat = feat
+        self.split_views()
+
+    def halo_rows_view(self, k: int) -> torch.Tensor:
+        return self._halo_symm[k * self._max_halo: k * self._max_halo + self.n_halo]
+
+    def aggregate_push(self, kernels, own, ns_own, ns_halo, rs, out, es=None, push_blocks=32):
+        """Two concurrent passes into a zero-filled ``out`` (vector red.add): the own-source pass on the
+        current stream; on a side stream the halo push (posted NVLink stores into the peers' symmetric halo
+        buffers), one device barrier, and the halo-source pass.  Double-buffered halo storage makes that
+        single barrier sufficient.  Each output element receives at most two addends -> deterministic."""
+        k = self._iter & 1
+        self._iter += 1
+        v_own, v_halo = self.split_views()
+        cur = torch.cuda.current_stream()
+        side = self._side
+        out.zero_()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _lib.call("stg_halo_push_f32", own.data_ptr(), self._feat, self.send_index.data_ptr(), self._send_peer.data_ptr(),
+                      self._send_slot.data_ptr(), int(self.send_index.numel()), self._push_ptrs[k], self.world,
+                      int(push_blocks), side.cuda_stream)
+            self._halo_hdl.barrier()                      # every rank's pushes for this step have landed
+            if self.n_halo > 0:
+                kernels.agg_scaled_sum(v_halo, self.halo_rows_view(k), ns_halo, es, rs, out=out, accumulate="red",
+                                       stream=side.cuda_stream)
+        kernels.agg_scaled_sum(v_own, own, ns_own, es, rs, out=out, accumulate="red")
+        cur.wait_stream(side)
+        return out
+
+    def profile_summary(self):
+        """Mean device time (ms) of each segment of aggregate_pull (set ``plan.profile = []`` to collect)."""
+        torch.cuda.synchronize()
+        names = ["barrier_in", "own_pass", "wait_pull", "halo_pass", "barrier_out"]
+        acc = {k: 0.0 for k in names + ["pull_kernel", "total"]}
+        for ev in self.profile:
+            for i, k in enumerate(names):
+                acc[k] += ev[i].elapsed_time(ev[i + 1])
+            acc["pull_kernel"] += ev[6].elapsed_time(ev[7])
+            acc["total"] += ev[0].elapsed_time(ev[5])
+        return {k: v / max(len(self.profile), 1) for k, v in acc.items()}
 
     # ------------------------------------------------------------------ buffers
     def new_buffer(self, feat: int, like: torch.Tensor) -> torch.Tensor:

@@ -28,7 +28,7 @@ def _check(t: torch.Tensor, name: str, dtype=torch.float32):
 
 
 def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
-                   out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+                   out: torch.Tensor | None = None, accumulate=False, stream=None) -> torch.Tensor:
     """``out[r] = row_scale[r] * sum_e nbr_scale[c_e] * edge_scale[eid_e] * x[c_e]`` (see ``stg_agg_scaled_sum_f32``)."""
     global launch_count
     _check(x, "x")
@@ -57,9 +57,9 @@ def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_
             raise ValueError(f"out must be [{n}, {feat}], got {tuple(out.shape)}")
     if n == 0 or feat == 0:
         return out
-    _lib.call("stg_agg_scaled_sum_accum_f32" if accumulate else "stg_agg_scaled_sum_f32", ctypes.byref(view),
-              x.data_ptr(), feat, _lib.ptr(nbr_scale), _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(),
-              _lib.current_stream_ptr())
+    fn = {False: "stg_agg_scaled_sum_f32", True: "stg_agg_scaled_sum_accum_f32", "red": "stg_agg_scaled_sum_red_f32"}[accumulate]
+    _lib.call(fn, ctypes.byref(view), x.data_ptr(), feat, _lib.ptr(nbr_scale), _lib.ptr(edge_scale), _lib.ptr(row_scale),
+              out.data_ptr(), stream if stream is not None else _lib.current_stream_ptr())
     launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
     return out
 

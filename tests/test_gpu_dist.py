@@ -65,3 +65,56 @@ def test_partitioned_source_blocks_reproduce_full_aggregation(cuda, world):
             kernels.agg_scaled_sum_parts(pg.fwd.view, ptrs, pg.fwd_bounds, feat, norm, None, norm[lo:hi].contiguous(), out=out)
             outs.append(out)
         assert torch.equal(torch.cat(outs), full), feat
+
+
+def test_two_concurrent_red_passes_are_deterministic_and_correct(cuda):
+    """Split every row's edges in two CSRs, run both passes concurrently with red.global.add into a zeroed buffer."""
+    from stgraph_b200 import _lib, kernels
+    from stgraph_b200.graph import StaticGraph
+    from stgraph_b200.utils import synthetic
+
+    n = 30000
+    src, dst = synthetic.power_law_graph(n, 600000, alpha=2.1, locality=0.5, window=512, max_degree=6000, seed=8, device=cuda)
+    g = StaticGraph(torch.stack([src, dst], 1), None, n)
+    F_ = g._forward_graph
+    norm = g.degree_norm().reshape(-1).contiguous()
+    x = torch.randn(n, 100, device=cuda)
+    full = kernels.agg_scaled_sum(g.fwd_view(), x, norm, None, norm)
+    mag = kernels.agg_scaled_sum(g.fwd_view(), x.abs(), norm, None, norm)
+    ro = F_.row_offset.long()
+    rows = torch.repeat_interleave(torch.arange(n, device=cuda), ro[1:] - ro[:-1])
+    mask = (torch.arange(rows.shape[0], device=cuda) % 3) != 0
+
+    def sub(m):
+        cnt = torch.bincount(rows[m], minlength=n)
+        sro = torch.zeros(n + 1, dtype=torch.int32, device=cuda)
+        sro[1:] = torch.cumsum(cnt, 0).int()
+        cols = F_.column_indices[m].contiguous()
+        v = _lib.StgCsrView()
+        v.row_offset, v.column_indices, v.eids, v.node_ids = sro.data_ptr(), cols.data_ptr(), None, None
+        v.num_nodes, v.num_edges, v.eid_base, v.eids_identity = n, int(cols.shape[0]), 0, 1
+        v.hub_rows = v.hub_count = None
+        v.hub_threshold = v.hub_capacity = 0
+        return v, (sro, cols)
+
+    va, ka = sub(mask)
+    vb, kb = sub(~mask)
+    side = torch.cuda.Stream()
+    results = []
+    for _ in range(4):
+        out = torch.zeros(n, 100, device=cuda)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            kernels.agg_scaled_sum(vb, x, norm, None, norm, out=out, accumulate="red", stream=side.cuda_stream)
+        kernels.agg_scaled_sum(va, x, norm, None, norm, out=out, accumulate="red")
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        results.append(out)
+    for r in results[1:]:
+        assert torch.equal(r, results[0])                 # two addends per element: order-independent
+    assert bool(((results[0] - full).abs() <= 2e-6 * mag + 1e-30).all())
+    # read-modify-write accumulate form, sequential
+    out = kernels.agg_scaled_sum(va, x, norm, None, norm)
+    kernels.agg_scaled_sum(vb, x, norm, None, norm, out=out, accumulate=True)
+    assert torch.equal(out, results[0])
