@@ -198,6 +198,7 @@ typedef struct StgVmProgram {
   int32_t n_tensors, n_instr, n_regs, n_acc;
   int32_t n_pre, n_loop;   /* instr[0,n_pre) PRE, [n_pre,n_pre+n_loop) LOOP, rest POST */
   float acc_init[STG_VM_MAX_ACC];
+  int32_t acc_kind[STG_VM_MAX_ACC];  /* 0 sum, 1 max, 2 min: how partial accumulators of a split hub row merge */
   StgVmTensor tensors[STG_VM_MAX_TENSORS];
   StgVmInstr instr[STG_VM_MAX_INSTR];
 } StgVmProgram;

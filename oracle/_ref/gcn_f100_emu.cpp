@@ -1,6 +1,6 @@
 #include "simt_shim.h"
-extern "C" void K2
-(float *Vedge_weight, float *Vhinb, float *Vnormcen, float *Vnorminb, float *V11, 
+extern "C" void K12
+(float *Vhinb, float *Vnormcen, float *Vnorminb, float *V96, 
   int *row_offsets,
   int *eids,
   int *column_indices,
@@ -22,28 +22,24 @@ extern "C" void K2
         
         for (; tx<feat_len; tx+=blockDim.x) {
             
-            float V10_tmp = 0;
-            int offset3 = dst_id * 7 + tx;int offset4 = dst_id * 1 + tx/7;
+            float V95_tmp = 0;
+            int offset2 = dst_id * 1 + tx/100;int offset3 = dst_id * 100 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 1 + tx/7;int offset1 = src_id * 7 + tx;int offset2 = eid * 1 + tx/7;
+                int offset0 = src_id * 1 + tx/100;int offset1 = src_id * 100 + tx;
                 
                 
                 
-                float V8_tmp = Vnorminb[offset0]*Vhinb[offset1];
-                
-                
-                
-                float V9_tmp = V8_tmp*Vedge_weight[offset2];
+                float V94_tmp = Vhinb[offset1]*Vnorminb[offset0];
                 
                 
                 
                 
-                V10_tmp += V9_tmp;
+                V95_tmp += V94_tmp;
                 
                 
             }
@@ -54,13 +50,13 @@ extern "C" void K2
             
             
             
-            float V11_tmp = V10_tmp*Vnormcen[offset4];
-            V11[offset3] = V11_tmp;
+            float V96_tmp = V95_tmp*Vnormcen[offset2];
+            V96[offset3] = V96_tmp;
             
         }
     }
-}extern "C" void K3
-(float *V12, float *Vedge_weight, float *Vnormcen, float *Vnorminb, float *V17, 
+}extern "C" void K13
+(float *V97, float *Vnormcen, float *Vnorminb, float *V101, 
   int *row_offsets,
   int *eids,
   int *column_indices,
@@ -82,28 +78,24 @@ extern "C" void K2
         
         for (; tx<feat_len; tx+=blockDim.x) {
             
-            float V16_tmp = 0;
-            int offset3 = src_id * 1 + tx/7;int offset4 = src_id * 7 + tx;
+            float V100_tmp = 0;
+            int offset2 = src_id * 1 + tx/100;int offset3 = src_id * 100 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = dst_id * 1 + tx/7;int offset1 = dst_id * 7 + tx;int offset2 = eid * 1 + tx/7;
+                int offset0 = dst_id * 100 + tx;int offset1 = dst_id * 1 + tx/100;
                 
                 
                 
-                float V13_tmp = V12[offset1]*Vnormcen[offset0];
-                
-                
-                
-                float V15_tmp = V13_tmp*Vedge_weight[offset2];
+                float V98_tmp = V97[offset0]*Vnormcen[offset1];
                 
                 
                 
                 
-                V16_tmp += V15_tmp;
+                V100_tmp += V98_tmp;
                 
                 
             }
@@ -114,26 +106,26 @@ extern "C" void K2
             
             
             
-            float V17_tmp = V16_tmp*Vnorminb[offset3];
-            V17[offset4] = V17_tmp;
+            float V101_tmp = V100_tmp*Vnorminb[offset2];
+            V101[offset3] = V101_tmp;
             
         }
     }
 }
 
-extern "C" void run_K2(void** t, int* row_offsets, int* eids, int* column_indices, int* node_ids,
+extern "C" void run_K12(void** t, int* row_offsets, int* eids, int* column_indices, int* node_ids,
     int num_nodes, int max_dimx, int max_dimy, int thrs_per_group, int nodes_per_block, int nblks, int nthrs) {
   blockDim.x = nthrs; blockDim.y = 1; blockDim.z = 1; gridDim.x = nblks;
   for (int b = 0; b < nblks; ++b) for (int th = 0; th < nthrs; ++th) {
     blockIdx.x = b; threadIdx.x = th;
-    K2((float*)t[0], (float*)t[1], (float*)t[2], (float*)t[3], (float*)t[4], row_offsets, eids, column_indices, node_ids, num_nodes, max_dimx, max_dimy, thrs_per_group, nodes_per_block);
+    K12((float*)t[0], (float*)t[1], (float*)t[2], (float*)t[3], row_offsets, eids, column_indices, node_ids, num_nodes, max_dimx, max_dimy, thrs_per_group, nodes_per_block);
   }
 }
-extern "C" void run_K3(void** t, int* row_offsets, int* eids, int* column_indices, int* node_ids,
+extern "C" void run_K13(void** t, int* row_offsets, int* eids, int* column_indices, int* node_ids,
     int num_nodes, int max_dimx, int max_dimy, int thrs_per_group, int nodes_per_block, int nblks, int nthrs) {
   blockDim.x = nthrs; blockDim.y = 1; blockDim.z = 1; gridDim.x = nblks;
   for (int b = 0; b < nblks; ++b) for (int th = 0; th < nthrs; ++th) {
     blockIdx.x = b; threadIdx.x = th;
-    K3((float*)t[0], (float*)t[1], (float*)t[2], (float*)t[3], (float*)t[4], row_offsets, eids, column_indices, node_ids, num_nodes, max_dimx, max_dimy, thrs_per_group, nodes_per_block);
+    K13((float*)t[0], (float*)t[1], (float*)t[2], (float*)t[3], row_offsets, eids, column_indices, node_ids, num_nodes, max_dimx, max_dimy, thrs_per_group, nodes_per_block);
   }
 }

@@ -199,7 +199,7 @@ def config3():
 def config4(scale=1.0):
     n = int(1_000_000 * scale)
     base, slide, T = int(10_000_000 * scale), int(100_000 * scale), 100
-    src, dst = synthetic.temporal_stream(n, base + slide * (T - 1) + 1000, alpha=1.8, seed=0, device=dev)
+    src, dst = synthetic.temporal_stream(n, base + slide * (T - 1), alpha=1.8, seed=0, device=dev)
     snaps = synthetic.sliding_window_snapshots(src, dst, base, slide, T)
     snaps = [torch.stack([s, d_], 1) for s, d_ in snaps]
     res = {"num_nodes": n, "snapshots": len(snaps)}

@@ -68,6 +68,7 @@ class StgVmProgram(Structure):
         ("n_pre", c_int32),
         ("n_loop", c_int32),
         ("acc_init", c_float * VM_MAX_ACC),
+        ("acc_kind", c_int32 * VM_MAX_ACC),
         ("tensors", StgVmTensor * VM_MAX_TENSORS),
         ("instr", StgVmInstr * VM_MAX_INSTR),
     ]

@@ -174,6 +174,7 @@ class _VmBuilder:
         self.reg_of = {}
         self.n_regs = 0
         self.acc_init = []
+        self.acc_kind = []
 
     def new_reg(self):
         r = self.n_regs
@@ -215,10 +216,75 @@ class _VmBuilder:
         self.reg_of[arg] = r
         return r
 
+    def _reuse_registers(self, seq):
+        """Linear-scan renaming of the virtual registers (they live in shared memory: fewer = more rows per SM).
+
+        A value defined before the edge loop and read inside it stays live until the loop ends; a value
+        defined inside the loop is dead after its last use in the same iteration.
+        """
+        n_pre, n_loop = len(self.instr[PRE]), len(self.instr[LOOP])
+        loop_end = n_pre + n_loop
+
+        def reads(ins):
+            op, _, dst, a, b, _ = ins
+            if op in (R.OP_LOAD, R.OP_CONST, R.OP_ACC_READ):
+                return []
+            if op in (R.OP_ACC_SUM, R.OP_ACC_MAX, R.OP_ACC_MIN):
+                return [a]
+            if op == R.OP_STORE:
+                return [b]
+            if op in (R.OP_ADD, R.OP_SUB, R.OP_MUL, R.OP_DIV, R.OP_RELU_BWD, R.OP_AMAX_BWD):
+                return [a, b]
+            return [a]          # unary ops, GSUM
+
+        def writes(ins):
+            op = ins[0]
+            if op in (R.OP_ACC_SUM, R.OP_ACC_MAX, R.OP_ACC_MIN, R.OP_STORE):
+                return None
+            return ins[2]
+
+        first_def, last_use = {}, {}
+        for i, ins in enumerate(seq):
+            for r in reads(ins):
+                last_use[r] = i
+            w = writes(ins)
+            if w is not None and w not in first_def:
+                first_def[w] = i
+        for r, d in first_def.items():
+            u = last_use.get(r, d)
+            if d < n_pre and n_pre <= u < loop_end:
+                u = loop_end                          # read in every iteration: stays live until the loop has ended
+            last_use[r] = max(u, d)
+        free, mapping, out, peak = [], {}, [], 0
+        expire = {}
+        for r, u in last_use.items():
+            expire.setdefault(u, []).append(r)
+        for i, ins in enumerate(seq):
+            op, ph, dst, a, b, imm = ins
+            rd = reads(ins)
+            na = mapping[a] if a in rd and a in mapping else a
+            nb = mapping[b] if b in rd and b in mapping else b
+            for r in expire.get(i, []):               # operands read here die here: their slot can hold the result
+                if r in mapping and first_def.get(r, -1) < i:
+                    free.append(mapping[r])
+            w = writes(ins)
+            nd = dst
+            if w is not None:
+                if w not in mapping:
+                    mapping[w] = free.pop() if free else peak
+                    if mapping[w] == peak:
+                        peak += 1
+                nd = mapping[w]
+                if last_use.get(w, i) == i and first_def.get(w) == i:
+                    free.append(mapping[w])           # never read
+            out.append((op, ph, nd, na, nb, imm))
+        return out, max(peak, 1)
+
     def finish(self):
         prog = _lib.StgVmProgram()
         prog.dim0, prog.dim1 = self.dims
         seq = self.instr[PRE] + self.instr[LOOP] + self.instr[POST]
+        seq, self.n_regs = self._reuse_registers(seq)
         if len(seq) > _lib.VM_MAX_INSTR:
             raise NotImplementedError("vertex program is longer than the VM kernel's instruction buffer")
         prog.n_tensors = len(self.tensors)
@@ -229,6 +295,7 @@ class _VmBuilder:
         prog.n_loop = len(self.instr[LOOP])
         for i, v in enumerate(self.acc_init):
             prog.acc_init[i] = v
+            prog.acc_kind[i] = self.acc_kind[i]
         for i, (side, bc0, bc1) in enumerate(self.tensor_meta):
             prog.tensors[i].side, prog.tensors[i].bc0, prog.tensors[i].bc1 = side, bc0, bc1
         for i, (op, ph, dst, a, b, imm) in enumerate(seq):
@@ -260,6 +327,7 @@ def _lower_vm(unit, center, targets, stmts):
             if k >= _lib.VM_MAX_ACC:
                 raise NotImplementedError("too many aggregations in one unit")
             b.acc_init.append(opdef.acc_init)
+            b.acc_kind.append({"aggmax": 1, "aggmin": 2}.get(name, 0))
             src = b.operand(st.args[0], LOOP)
             b.emit(LOOP, opdef.vm_op, dst=k, a=src)
             acc_of[st.ret] = k

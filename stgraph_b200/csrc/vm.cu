@@ -20,6 +20,11 @@ namespace stg {
 namespace {
 
 constexpr int kVmThreads = 128;
+constexpr int kVmHubThreads = 1024;   // one block per long row: 32 warps share its edges
+
+// Rows longer than this are split over a whole block (interpreting an instruction costs a few hundred
+// cycles, so long rows dominate otherwise).  The hub launch finds them by scanning the row lengths itself.
+constexpr int kVmHubThreshold = 96;
 
 struct VmArgs {
   StgCsrView g;
@@ -33,25 +38,41 @@ __device__ __forceinline__ int tensor_size(const StgVmTensor& t, int dim0, int d
   return (t.bc0 ? dim0 : 1) * (t.bc1 ? dim1 : 1);
 }
 
-template <int GROUP>
-__global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ VmArgs a,
-                                                        const __grid_constant__ StgVmProgram prog) {
+// HUB = false: one lane group per row (rows longer than the view's hub threshold are skipped).
+// HUB = true : one BLOCK per hub row; every (warp, group) slot takes a strided share of the row's edges,
+//              the accumulators are merged through shared memory by kind (sum / max / min) in a fixed
+//              order, and slot 0 alone runs the POST phase.
+template <int GROUP, bool HUB>
+__global__ void __launch_bounds__(HUB ? kVmHubThreads : kVmThreads)
+    vm_kernel(const __grid_constant__ VmArgs a, const __grid_constant__ StgVmProgram prog) {
+  constexpr int NT = HUB ? kVmHubThreads : kVmThreads;     // threads per block
   extern __shared__ float smem[];
-  float* regs = smem;                                      // [n_regs][kVmThreads]
-  float* accs = smem + prog.n_regs * kVmThreads;           // [n_acc][kVmThreads]
-  float* scratch = accs + prog.n_acc * kVmThreads;         // [kVmThreads] lane-reduction staging
+  float* regs = smem;                                      // [n_regs][NT]
+  float* accs = smem + prog.n_regs * NT;                   // [n_acc][NT]
+  float* scratch = accs + prog.n_acc * NT;                 // [NT] lane-reduction staging
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int gl = lane & (GROUP - 1);
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
-  const int warp = blockIdx.x * (kVmThreads / 32) + (tid >> 5);
-  const int row = warp * GROUPS_PER_WARP + lane / GROUP;
-  if (row >= a.g.num_nodes) return;
+  constexpr int NSLOT = HUB ? (NT / 32) * GROUPS_PER_WARP : 1;
+  const int slot = HUB ? (tid >> 5) * GROUPS_PER_WARP + lane / GROUP : 0;
   const int lanes = prog.dim0 * prog.dim1;
   const int dim1 = prog.dim1;
+  const int n_iter = HUB ? a.g.num_nodes : 1;
+  for (int it = HUB ? blockIdx.x : 0; it < n_iter; it += HUB ? gridDim.x : 1) {
+  int row;
+  if (HUB) {
+    row = it;
+  } else {
+    const int warp = blockIdx.x * (kVmThreads / 32) + (tid >> 5);
+    row = warp * GROUPS_PER_WARP + lane / GROUP;
+    if (row >= a.g.num_nodes) return;
+  }
   const int beg = __ldg(a.g.row_offset + row);
   const int end = __ldg(a.g.row_offset + row + 1);
+  if (HUB && (end - beg) <= kVmHubThreshold) continue;    // block-uniform: every thread sees the same row
+  if (!HUB && (end - beg) > kVmHubThreshold) return;      // the hub launch owns this row
   const bool seg_pow2 = (dim1 & (dim1 - 1)) == 0 && dim1 <= GROUP;
   // lanes per chunk: whole dim1-segments only, so a segment never straddles two chunks
   const int chunk = (dim1 <= GROUP) ? (GROUP / dim1) * dim1 : GROUP;
@@ -69,8 +90,8 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
     return s;
   };
 
-#define R(i) regs[(i) * kVmThreads + tid]
-#define ACC(i) accs[(i) * kVmThreads + tid]
+#define R(i) regs[(i) * NT + tid]
+#define ACC(i) accs[(i) * NT + tid]
 
   for (int tx0 = 0; tx0 < lanes; tx0 += chunk) {
     const int tx = tx0 + gl;
@@ -150,13 +171,31 @@ __global__ void __launch_bounds__(kVmThreads) vm_kernel(const __grid_constant__ 
     for (; pc < prog.n_pre; ++pc) exec(prog.instr[pc]);
     const int loop_end = prog.n_pre + prog.n_loop;
     if (prog.n_loop > 0) {
-      for (int e = beg; e < end; ++e) {
+      for (int e = beg + slot; e < end; e += NSLOT) {
         nbr = __ldg(a.g.column_indices + e);
         eid = a.g.eids_identity ? e : (__ldg(a.g.eids + e) - a.g.eid_base);
         for (int q = prog.n_pre; q < loop_end; ++q) exec(prog.instr[q]);
       }
     }
-    for (int q = loop_end; q < prog.n_instr; ++q) exec(prog.instr[q]);
+    if (HUB) {
+      __syncthreads();
+      if (slot == 0) {
+        for (int k = 0; k < prog.n_acc; ++k) {
+          float v = ACC(k);
+          for (int s2 = 1; s2 < NSLOT; ++s2) {
+            const int other = (s2 / GROUPS_PER_WARP) * 32 + (s2 % GROUPS_PER_WARP) * GROUP + gl;
+            const float o = accs[k * NT + other];
+            v = prog.acc_kind[k] == 1 ? fmaxf(v, o) : prog.acc_kind[k] == 2 ? fminf(v, o) : v + o;
+          }
+          ACC(k) = v;
+        }
+        for (int q = loop_end; q < prog.n_instr; ++q) exec(prog.instr[q]);
+      }
+      __syncthreads();
+    } else {
+      for (int q = loop_end; q < prog.n_instr; ++q) exec(prog.instr[q]);
+    }
+  }
   }
 #undef R
 #undef ACC
@@ -167,8 +206,19 @@ int launch_vm(const VmArgs& a, const StgVmProgram& prog, cudaStream_t stream) {
   const int rows_per_block = (kVmThreads / 32) * (32 / GROUP);
   const int blocks = (a.g.num_nodes + rows_per_block - 1) / rows_per_block;
   const size_t smem = static_cast<size_t>(prog.n_regs + prog.n_acc + 1) * kVmThreads * sizeof(float);
-  vm_kernel<GROUP><<<blocks, kVmThreads, smem, stream>>>(a, prog);
+  vm_kernel<GROUP, false><<<blocks, kVmThreads, smem, stream>>>(a, prog);
   STG_LAUNCH_CHECK("vm_kernel");
+  if (a.g.num_edges > kVmHubThreshold) {     // a row longer than the threshold can only exist then
+    const size_t hub_smem = static_cast<size_t>(prog.n_regs + prog.n_acc + 1) * kVmHubThreads * sizeof(float);
+    static size_t configured = 0;
+    if (hub_smem > configured) {
+      STG_CUDA(cudaFuncSetAttribute(vm_kernel<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(hub_smem)));
+      configured = hub_smem;
+    }
+    vm_kernel<GROUP, true><<<2 * sm_count(), kVmHubThreads, hub_smem, stream>>>(a, prog);
+    STG_LAUNCH_CHECK("vm_kernel(hub)");
+  }
   return STG_OK;
 }
 

@@ -322,6 +322,9 @@ class KeyedDynamicGraph(DynamicGraph):
         if self._views_valid and (self._views_have_backward or not need_backward):
             return
         want_bwd = need_backward or self._is_backprop_state
+        # views already handed out (StgCsrView structs hold raw pointers) must stay valid until the snapshot
+        # changes: park the objects being replaced instead of dropping them
+        self._retired = [self._forward_graph, self._backward_graph] if self._views_valid else []
         self._forward_graph, bwd = build_views(self._keys, self.max_num_nodes, self._descending_rows, self._label_base,
                                                want_bwd)
         self._backward_graph = bwd

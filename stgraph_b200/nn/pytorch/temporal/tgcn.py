@@ -76,9 +76,11 @@ class TGCN(torch.nn.Module):
         return Z * H + (1 - Z) * H_tilde
 
     def forward(self, g, X, edge_weight=None, H=None):
-        H = self._set_hidden_state(X, H)
         if self.fused:
+            if H is None:      # allocated on the device directly: no H2D copy, CUDA-graph capturable
+                H = torch.zeros(X.shape[0], self.out_channels, device=X.device, dtype=X.dtype)
             return self._forward_fused(g, X, edge_weight, H)
+        H = self._set_hidden_state(X, H)
         Z = self._calculate_update_gate(g, X, edge_weight, H)
         R = self._calculate_reset_gate(g, X, edge_weight, H)
         H_tilde = self._calculate_candidate_state(g, X, edge_weight, H, R)

@@ -38,6 +38,7 @@ def gcn_aggregate(graph, h, norm, edge_weight=None):
     """Differentiable w.r.t. ``h`` only (like the reference: no gradient for ``norm`` / ``edge_weight``)."""
     if not h.is_cuda:
         raise RuntimeError("h must live on a CUDA device (stgraph_b200 has no CPU path)")
-    fwd, bwd = graph.fwd_view(), graph.bwd_view()
+    bwd = graph.bwd_view()            # backward first: a dynamic graph builds both views in one go
+    fwd = graph.fwd_view()
     keep = (graph._forward_graph, graph._backward_graph)
     return _GcnAggregate.apply(fwd, bwd, keep, h, norm, edge_weight)

@@ -187,15 +187,23 @@ def products_shaped(seed: int = 0, device="cpu", scale: float = 1.0, locality: f
 
 
 def temporal_stream(num_nodes: int, num_events: int, alpha: float = 1.8, seed: int = 0, device="cpu"):
-    """Config 4 input: a stream of temporal edges with Zipf endpoints (sx-mathoverflow / wiki-talk shaped)."""
+    """Config 4 input: exactly ``num_events`` temporal edges with Zipf endpoints, no self loops
+    (sx-mathoverflow / wiki-talk shaped; repeated interactions are frequent, snapshots de-duplicate them)."""
     g = _gen(seed, device)
-    w = _zipf_weights(num_nodes, max(alpha, 1.05) + 1e-9 if alpha <= 1 else alpha, None, g, device)
+    w = _zipf_weights(num_nodes, alpha, None, g, device)
     cdf = torch.cumsum(w, 0)
     cdf = cdf / cdf[-1]
-    u = _sample(cdf, num_events, g, device)
-    v = _sample(cdf, num_events, g, device)
-    keep = u != v
-    return u[keep].to(torch.int32), v[keep].to(torch.int32)
+    us, vs, have = [], [], 0
+    while have < num_events:
+        k = int((num_events - have) * 1.05) + 1024
+        u = _sample(cdf, k, g, device)
+        v = _sample(cdf, k, g, device)
+        keep = u != v
+        us.append(u[keep])
+        vs.append(v[keep])
+        have += int(keep.sum())
+    u, v = torch.cat(us)[:num_events], torch.cat(vs)[:num_events]
+    return u.to(torch.int32), v.to(torch.int32)
 
 
 def sliding_window_snapshots(src, dst, base: int, slide: int, num_snapshots: int | None = None):

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.StgCsrView) == 4 * 8 + 4 * 4 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.StgVmInstr) == 16
     assert ctypes.sizeof(_lib.StgVmTensor) == 16
-    assert ctypes.sizeof(_lib.StgVmProgram) == 8 * 4 + 4 * _lib.VM_MAX_ACC + 16 * _lib.VM_MAX_TENSORS + 16 * _lib.VM_MAX_INSTR
+    assert ctypes.sizeof(_lib.StgVmProgram) == 8 * 4 + 8 * _lib.VM_MAX_ACC + 16 * _lib.VM_MAX_TENSORS + 16 * _lib.VM_MAX_INSTR
 
 
 def test_argument_validation_without_gpu():
