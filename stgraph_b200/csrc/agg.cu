@@ -23,6 +23,8 @@
 //   4*(2*N*F + E + (N+1) + 2*N [+ E for edge_scale]).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace stg {
 namespace {
 
@@ -184,30 +186,42 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   }
 }
 
-// Block per hub row: every (warp, group) pair takes a strided share of the row's
-// edge batches; partials are reduced group->warp by shuffles and warp->block
-// through shared memory in a fixed order.
+// Cluster per hub row: a thread-block cluster of kHubCluster CTAs (kHubCluster x 16 warps) owns one
+// hub row.  Every (CTA, warp, group) slot takes a strided share of the row's edge batches; partials are
+// reduced group->warp by shuffles, warp->CTA through shared memory, and CTA->cluster by the leader CTA
+// reading its peers' shared memory (DSMEM), each level in a fixed order: deterministic, no atomics, no
+// scratch buffer in HBM.  A power-law graph has a few rows with 10^4..10^5 edges; one CTA per such row
+// left most of the chip idle (the hub kernel cost as much as the main kernel on the config-4 stream).
+constexpr int kHubCluster = 8;
+
 template <int VEC, int GROUP, int NACC>
-__global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p) {
+__global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThreads)
+    agg_hub_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
   constexpr int WARPS = kHubThreads / 32;
   __shared__ T partial[WARPS][GROUP * NACC];
+  __shared__ T cta_sum[GROUP * NACC];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int gl = lane & (GROUP - 1);
   const int gidx = lane / GROUP;
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
+  const int crank = static_cast<int>(cluster.block_rank());
+  const int cluster_id = blockIdx.x / kHubCluster;
+  const int n_clusters = gridDim.x / kHubCluster;
   const int n_hub = min(__ldg(p.hub_count), p.hub_capacity);
-  for (int i = blockIdx.x; i < n_hub; i += gridDim.x) {
+  for (int i = cluster_id; i < n_hub; i += n_clusters) {
     const int row = __ldg(p.hub_rows + i);
     const int beg = __ldg(p.row_off + row);
     const int end = __ldg(p.row_off + row + 1);
     T acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-    accumulate_edges<VEC, GROUP, NACC>(p, beg, end, wid * GROUPS_PER_WARP + gidx,
-                                       WARPS * GROUPS_PER_WARP, gl, gmask, acc);
+    accumulate_edges<VEC, GROUP, NACC>(p, beg, end, (crank * WARPS + wid) * GROUPS_PER_WARP + gidx,
+                                       kHubCluster * WARPS * GROUPS_PER_WARP, gl, gmask, acc);
     // groups of one warp -> lanes [0, GROUP)
 #pragma unroll
     for (int o = GROUP; o < 32; o <<= 1) {
@@ -233,13 +247,25 @@ __global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p)
       for (int k = 0; k < NACC; ++k) partial[wid][k * GROUP + lane] = acc[k];
     }
     __syncthreads();
-    if (wid == 0 && lane < GROUP) {
-      const float r = p.rs ? __ldg(p.rs + row) : 1.f;
-      float* dst = p.out + static_cast<size_t>(row) * p.ld;
+    if (wid == 0 && lane < GROUP) {               // warps of this CTA, fixed order
 #pragma unroll
       for (int k = 0; k < NACC; ++k) {
         T sum = partial[0][k * GROUP + lane];
         for (int w = 1; w < WARPS; ++w) add_vec(sum, partial[w][k * GROUP + lane]);
+        cta_sum[k * GROUP + lane] = sum;
+      }
+    }
+    cluster.sync();                               // every CTA's cta_sum is written
+    if (crank == 0 && wid == 0 && lane < GROUP) { // CTAs of the cluster, fixed order, over DSMEM
+      const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+      float* dst = p.out + static_cast<size_t>(row) * p.ld;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        T sum = cta_sum[k * GROUP + lane];
+        for (int c = 1; c < kHubCluster; ++c) {
+          const T* remote = cluster.map_shared_rank(cta_sum, c);
+          add_vec(sum, remote[k * GROUP + lane]);
+        }
         const int o = (lane + k * GROUP) * VEC;
         if (o < p.width) {
           scale_vec(sum, r);
@@ -252,7 +278,7 @@ __global__ void __launch_bounds__(kHubThreads) agg_hub_kernel(const AggParams p)
         }
       }
     }
-    __syncthreads();
+    cluster.sync();                               // peers keep cta_sum alive until the leader has read it
   }
 }
 
@@ -265,7 +291,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
     STG_LAUNCH_CHECK("agg_rows_kernel");
   }
   if (p.hub_threshold > 0 && p.hub_rows != nullptr) {
-    agg_hub_kernel<VEC, GROUP, NACC><<<2 * sm_count(), kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC><<<(sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   return STG_OK;
