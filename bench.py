@@ -457,7 +457,7 @@ def main():
                        "halo": halo_info, "partitioned_result_matches_single_gpu": parity,
                        "scale": args.scale},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "agg_rows_kernel<4,32,1> (forward, in-edge CSR)",
+                         "traffic": ncu_traffic(), "kernel": "agg_rows_pipe_kernel<4,32,1,4,8> + agg_hub_kernel<4,32,1> overlapped (forward, in-edge CSR)",
                          "kernel_ms": ms_fwd_kernel, "algorithmic_bytes": b_alg_one, "peak_source": peak_src,
                          "gather_model_gbs": 4.0 * (e * FEAT + n * FEAT + e) / (ms_fwd_kernel * 1e-3) / 1e9},
             "gpu_launches": launches, "clocks": clocks,

@@ -49,6 +49,7 @@ struct AggParams {
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ hub_count;
   int num_rows;
+  int num_edges;
   int eid_base;
   int eids_identity;
   int hub_threshold;
@@ -82,14 +83,41 @@ __device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
   return p.xs[o] + static_cast<size_t>(c - p.bounds[o]) * p.ld;
 }
 
+// The row kernels run as programmatic dependents of the hub kernel (both in flight at once); a row
+// kernel block does not retire before the hub kernel has completed and flushed, so "row kernel
+// complete" implies "hub rows written" for whatever follows in the stream.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Column index and combined scale of edge `base + gl` (0 / 0.f past the end of the row).
+__device__ __forceinline__ void load_col(const AggParams& p, int base, int end, int gl, int& c) {
+  c = 0;
+  const int e = base + gl;
+  if (e < end) c = ld_stream(p.col + e);
+}
+__device__ __forceinline__ void load_scale(const AggParams& p, int base, int end, int gl, int c, float& s) {
+  s = 0.f;
+  const int e = base + gl;
+  if (e < end) {
+    float sc = 1.f;
+    if (p.ns) sc = __ldg(p.ns + c);
+    if (p.es) {
+      const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
+      sc *= __ldg(p.es + eid);
+    }
+    s = sc;
+  }
+}
+
 // Accumulate edges [beg,end) visited with stride `step` batches of GROUP edges,
 // starting at batch `first`.  All lanes of a group execute this together.
-template <int VEC, int GROUP, int NACC>
+// (my_c, my_s) = column / scale of the first batch, loaded by the caller (so that a caller can
+// have them in flight long before the row is processed).
+template <int VEC, int GROUP, int NACC, int UNROLL_ = 0>
 __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
                                                  int batch_step, int gl, unsigned gmask,
-                                                 typename VecT<VEC>::type (&acc)[NACC]) {
+                                                 typename VecT<VEC>::type (&acc)[NACC], int my_c, float my_s) {
   using T = typename VecT<VEC>::type;
-  constexpr int UNROLL = (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
+  constexpr int UNROLL = UNROLL_ > 0 ? (UNROLL_ < GROUP ? UNROLL_ : GROUP) : (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
   bool act[NACC];
   int off[NACC];
 #pragma unroll
@@ -98,28 +126,12 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
     act[k] = off[k] < p.width;
   }
 
-  auto load_meta = [&](int base, int& c, float& s) {
-    c = 0;
-    s = 0.f;
-    const int e = base + gl;
-    if (e < end) {
-      c = ld_stream(p.col + e);
-      float sc = 1.f;
-      if (p.ns) sc = __ldg(p.ns + c);
-      if (p.es) {
-        const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
-        sc *= __ldg(p.es + eid);
-      }
-      s = sc;
-    }
-  };
-
   int base = beg + first_batch * GROUP;
-  int my_c, nx_c;
-  float my_s, nx_s;
-  load_meta(base, my_c, my_s);
+  int nx_c;
+  float nx_s;
   for (; base < end; base += batch_step * GROUP) {
-    load_meta(base + batch_step * GROUP, nx_c, nx_s);   // prefetch next batch
+    load_col(p, base + batch_step * GROUP, end, gl, nx_c);   // prefetch next batch
+    load_scale(p, base + batch_step * GROUP, end, gl, nx_c, nx_s);
     const int n = min(GROUP, end - base);
     for (int j = 0; j < n; j += UNROLL) {
       int c[UNROLL];
@@ -151,6 +163,118 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
 }
 
 template <int VEC, int GROUP, int NACC>
+__device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
+                                                 int batch_step, int gl, unsigned gmask,
+                                                 typename VecT<VEC>::type (&acc)[NACC]) {
+  int c;
+  float s;
+  load_col(p, beg + first_batch * GROUP, end, gl, c);
+  load_scale(p, beg + first_batch * GROUP, end, gl, c, s);
+  accumulate_edges<VEC, GROUP, NACC>(p, beg, end, first_batch, batch_step, gl, gmask, acc, c, s);
+}
+
+// Scaled row result -> out (assign / += / red.add).
+template <int VEC, int GROUP, int NACC>
+__device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, bool nonempty, float r,
+                                          typename VecT<VEC>::type (&acc)[NACC]) {
+  using T = typename VecT<VEC>::type;
+  float* dst = p.out + static_cast<size_t>(row) * p.ld;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    const int o = (gl + k * GROUP) * VEC;
+    if (o < p.width) {
+      scale_vec(acc[k], r);
+      if (p.accumulate == 2) {
+        if (nonempty) red_add(dst + o, acc[k]);
+        continue;
+      }
+      if (p.accumulate) add_vec(acc[k], *reinterpret_cast<const T*>(dst + o));
+      st_row<VEC>(dst + o, acc[k]);
+    }
+  }
+}
+
+// Software-pipelined row queue.  A block owns `slots_per_block` consecutive row slots (a slot =
+// 32/GROUP rows, one per lane group); its warps draw slots from a shared-memory counter, so a warp
+// that got short rows simply takes more of them (one-row-per-warp blocks idle 1/3 of their warp slots
+// on a power-law graph: every block waits for its longest row).  The dependent load chain of a row
+// (row_offset -> column index -> neighbour scale -> neighbour rows) is spread over four consecutive
+// loop iterations: while row i is being summed, the scales of row i+1, the columns of row i+2 and
+// the offsets of row i+3 are already in flight.
+template <int VEC, int GROUP, int NACC, int MINB, int UNROLL>
+__global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(const AggParams p, int slots_per_block) {
+  using T = typename VecT<VEC>::type;
+  constexpr int GPW = 32 / GROUP;
+  __shared__ int next_slot;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (GROUP - 1);
+  const int gidx = lane / GROUP;
+  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
+  const int total_slots = (p.num_rows + GPW - 1) / GPW;
+  const int first = blockIdx.x * slots_per_block;
+  const int last = min(first + slots_per_block, total_slots);
+  if (threadIdx.x == 0) next_slot = first;
+  __syncthreads();
+
+  auto draw = [&]() {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(&next_slot, 1);
+    return __shfl_sync(0xffffffffu, s, 0);
+  };
+  // stage A: slot -> row, [beg, end); row = -1 when there is nothing to do (past the end, hub row)
+  auto stage_a = [&](int slot, int& row, int& beg, int& end) {
+    row = slot * GPW + gidx;
+    beg = end = 0;
+    if (slot >= last || row >= p.num_rows) { row = -1; return; }
+    beg = __ldg(p.row_off + row);
+    end = __ldg(p.row_off + row + 1);
+  };
+
+  int slot0, row0, beg0, end0, c0;     // row being summed (scale loaded at the top of the iteration)
+  int row1, beg1, end1, c1;            // columns in flight
+  int row2, beg2, end2;                // offsets in flight
+  float s0, r0;
+  slot0 = draw();
+  if (slot0 >= last) return;
+  stage_a(slot0, row0, beg0, end0);
+  int slot1 = draw();
+  stage_a(slot1, row1, beg1, end1);
+  int slot2 = draw();
+  stage_a(slot2, row2, beg2, end2);
+  if (row0 >= 0 && p.hub_threshold > 0 && (end0 - beg0) > p.hub_threshold) row0 = -1, end0 = beg0;
+  load_col(p, beg0, end0, gl, c0);
+  if (row1 >= 0 && p.hub_threshold > 0 && (end1 - beg1) > p.hub_threshold) row1 = -1, end1 = beg1;
+  load_col(p, beg1, end1, gl, c1);
+  load_scale(p, beg0, end0, gl, c0, s0);
+  r0 = (row0 >= 0 && p.rs) ? __ldg(p.rs + row0) : 1.f;
+
+  while (slot0 < last) {
+    // issue the loads of the three younger stages before touching the current row
+    const int slot3 = draw();
+    int row3, beg3, end3;
+    stage_a(slot3, row3, beg3, end3);
+    if (row2 >= 0 && p.hub_threshold > 0 && (end2 - beg2) > p.hub_threshold) row2 = -1, end2 = beg2;
+    int c2;
+    load_col(p, beg2, end2, gl, c2);
+    float s1;
+    load_scale(p, beg1, end1, gl, c1, s1);
+    const float r1 = (row1 >= 0 && p.rs) ? __ldg(p.rs + row1) : 1.f;
+
+    if (row0 >= 0) {
+      T acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+      accumulate_edges<VEC, GROUP, NACC, UNROLL>(p, beg0, end0, 0, 1, gl, gmask, acc, c0, s0);
+      write_row<VEC, GROUP, NACC>(p, row0, gl, end0 > beg0, r0, acc);
+    }
+    slot0 = slot1; row0 = row1; beg0 = beg1; end0 = end1; c0 = c1; s0 = s1; r0 = r1;
+    slot1 = slot2; row1 = row2; beg1 = beg2; end1 = end2; c1 = c2;
+    slot2 = slot3; row2 = row3; beg2 = beg3; end2 = end3;
+  }
+  grid_dependency_wait();
+}
+
+template <int VEC, int GROUP, int NACC>
 __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
@@ -170,20 +294,8 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   accumulate_edges<VEC, GROUP, NACC>(p, beg, end, 0, 1, gl, gmask, acc);
 
   const float r = p.rs ? __ldg(p.rs + row) : 1.f;
-  float* dst = p.out + static_cast<size_t>(row) * p.ld;
-#pragma unroll
-  for (int k = 0; k < NACC; ++k) {
-    const int o = (gl + k * GROUP) * VEC;
-    if (o < p.width) {
-      scale_vec(acc[k], r);
-      if (p.accumulate == 2) {
-        if (end > beg) red_add(dst + o, acc[k]);
-        continue;
-      }
-      if (p.accumulate) add_vec(acc[k], *reinterpret_cast<const T*>(dst + o));
-      st_row<VEC>(dst + o, acc[k]);
-    }
-  }
+  write_row<VEC, GROUP, NACC>(p, row, gl, end > beg, r, acc);
+  grid_dependency_wait();
 }
 
 // Cluster per hub row: a thread-block cluster of kHubCluster CTAs (kHubCluster x 16 warps) owns one
@@ -199,6 +311,9 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
     agg_hub_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
   namespace cg = cooperative_groups;
+  // The row kernel is launched behind this one as a programmatic dependent (see launch_agg): let it
+  // start right away, the two kernels write disjoint rows.
+  asm volatile("griddepcontrol.launch_dependents;");
   cg::cluster_group cluster = cg::this_cluster();
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
   constexpr int WARPS = kHubThreads / 32;
@@ -282,17 +397,53 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
   }
 }
 
+// Launch `kernel` so that it may start while the previous kernel of the stream is still running
+// (programmatic dependent launch); the kernel orders itself with grid_dependency_wait().
+template <typename... KArgs, typename... Args>
+cudaError_t launch_overlapped(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t stream, bool overlap,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int VEC, int GROUP, int NACC>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
   const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > 0) {
-    agg_rows_kernel<VEC, GROUP, NACC><<<blocks, kBlockThreads, 0, stream>>>(p);
-    STG_LAUNCH_CHECK("agg_rows_kernel");
-  }
-  if (p.hub_threshold > 0 && p.hub_rows != nullptr) {
+  // Hub rows first: one cluster per row, at most one CTA per SM; the row kernel then fills the rest of
+  // every SM instead of waiting for the last hub row (0.27 ms of a 3.5 ms launch on config 5).
+  const bool hubs = p.hub_threshold > 0 && p.hub_rows != nullptr;
+  // Small graphs gain nothing from the overlap and a programmatic edge costs extra inside a captured CUDA
+  // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
+  const bool overlap = hubs && p.num_edges >= (1 << 20);
+  if (hubs) {
     agg_hub_kernel<VEC, GROUP, NACC><<<(sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
+  }
+  if (blocks > 0) {
+    if constexpr (GROUP == 32) {
+      // measured on config 5 (F=100 / 128): 3.48 / 3.34 ms against 3.99 / 3.88 ms for one row per warp;
+      // 4 resident blocks per SM beat 3 (4.2 ms) and 2 (5.2 ms), 5..8 with a shorter unroll do not help.
+      constexpr int kRowsPerWarp = 32;
+      constexpr int MINB = 4;           // 8 / NACC neighbour rows in flight per lane keep this at <= 64 registers
+      constexpr int slots_per_block = (kBlockThreads / 32) * kRowsPerWarp;
+      const int pblocks = (p.num_rows + slots_per_block - 1) / slots_per_block;
+      STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC>, pblocks, kBlockThreads, stream,
+                                 overlap, p, slots_per_block));
+    } else {
+      // narrow rows (several rows per warp): the lane groups of a warp diverge and the queue costs
+      // more than it saves (F=64: 3.0 ms against 2.66 ms)
+      STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC>, blocks, kBlockThreads, stream, overlap, p));
+    }
+    STG_LAUNCH_CHECK("agg_rows_kernel");
   }
   return STG_OK;
 }
@@ -329,6 +480,7 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   p.hub_rows = g->hub_rows;
   p.hub_count = g->hub_count;
   p.num_rows = g->num_nodes;
+  p.num_edges = g->num_edges;
   p.eid_base = g->eid_base;
   p.eids_identity = g->eids_identity;
   p.hub_threshold = (g->hub_rows && g->hub_count) ? g->hub_threshold : 0;
