@@ -69,14 +69,13 @@ struct AggParams {
   const float* xs[STG_MAX_PARTS];
 };
 
-// Address of source row c: local matrix, or the owner's block when the matrix is partitioned.
 // out += v with a vector reduction (red.global.add.v4.f32 on sm_90+): no read round trip
 __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void red_add(float* p, float2 v) { atomicAdd(reinterpret_cast<float2*>(p), v); }
 __device__ __forceinline__ void red_add(float* p, float4 v) { atomicAdd(reinterpret_cast<float4*>(p), v); }
 
+// Address of source row c in the owner's block of a row-partitioned matrix.
 __device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
-  if (p.nparts == 0) return p.x + static_cast<size_t>(c) * p.ld;
   int o = 0;
 #pragma unroll
   for (int q = 1; q < STG_MAX_PARTS; ++q) o += (q < p.nparts && c >= p.bounds[q]) ? 1 : 0;
@@ -112,19 +111,46 @@ __device__ __forceinline__ void load_scale(const AggParams& p, int base, int end
 // starting at batch `first`.  All lanes of a group execute this together.
 // (my_c, my_s) = column / scale of the first batch, loaded by the caller (so that a caller can
 // have them in flight long before the row is processed).
-template <int VEC, int GROUP, int NACC, int UNROLL_ = 0>
+// Neighbour-row loads of one lane: lane column offsets are clamped into the row (lanes past `width`
+// re-read column 0 and their sums are never written), so the steady state carries no per-load
+// predicate, and a row address is ONE IMAD.WIDE off a per-lane base pointer.  PARTS = source matrix
+// row-partitioned over peer GPUs (cold path, stg_agg_scaled_sum_parts_f32).
+template <int VEC, int GROUP, int NACC, bool PARTS>
+struct RowLoader {
+  using T = typename VecT<VEC>::type;
+  const char* base[NACC];
+  int off[NACC];
+  unsigned ld_bytes;
+  __device__ __forceinline__ RowLoader(const AggParams& p, int gl) {
+    ld_bytes = static_cast<unsigned>(p.ld) * 4u;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      int o = (gl + k * GROUP) * VEC;
+      if (o >= p.width) o = 0;
+      off[k] = o;
+      base[k] = reinterpret_cast<const char*>(p.x + o);
+    }
+  }
+  __device__ __forceinline__ T load(const AggParams& p, int c, int k) const {
+    if constexpr (PARTS) {
+      return ld_row<VEC>(src_row(p, c) + off[k]);
+    } else {
+      return __ldg(reinterpret_cast<const T*>(base[k] + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
+    }
+  }
+};
+
+// Accumulate edges [beg,end) visited with stride `step` batches of GROUP edges,
+// starting at batch `first`.  All lanes of a group execute this together.
+// (my_c, my_s) = column / scale of the first batch, loaded by the caller (so that a caller can
+// have them in flight long before the row is processed).
+template <int VEC, int GROUP, int NACC, int UNROLL_ = 0, bool PARTS = false>
 __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
                                                  int batch_step, int gl, unsigned gmask,
                                                  typename VecT<VEC>::type (&acc)[NACC], int my_c, float my_s) {
   using T = typename VecT<VEC>::type;
   constexpr int UNROLL = UNROLL_ > 0 ? (UNROLL_ < GROUP ? UNROLL_ : GROUP) : (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
-  bool act[NACC];
-  int off[NACC];
-#pragma unroll
-  for (int k = 0; k < NACC; ++k) {
-    off[k] = (gl + k * GROUP) * VEC;
-    act[k] = off[k] < p.width;
-  }
+  const RowLoader<VEC, GROUP, NACC, PARTS> rows(p, gl);
 
   int base = beg + first_batch * GROUP;
   int nx_c;
@@ -133,7 +159,8 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
     load_col(p, base + batch_step * GROUP, end, gl, nx_c);   // prefetch next batch
     load_scale(p, base + batch_step * GROUP, end, gl, nx_c, nx_s);
     const int n = min(GROUP, end - base);
-    for (int j = 0; j < n; j += UNROLL) {
+    int j = 0;
+    for (; j + UNROLL <= n; j += UNROLL) {     // full groups: UNROLL unpredicated row loads in flight
       int c[UNROLL];
       float s[UNROLL];
       T v[UNROLL][NACC];
@@ -144,10 +171,29 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const float* src = src_row(p, c[u]);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) v[u][k] = rows.load(p, c[u], k);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], s[u], v[u][k]);
+      }
+    }
+    if (j < n) {                               // last, partial group of the batch
+      int c[UNROLL];
+      float s[UNROLL];
+      T v[UNROLL][NACC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        c[u] = __shfl_sync(gmask, my_c, j + u, GROUP);
+        s[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
-          if (act[k] && (j + u) < n) v[u][k] = ld_row<VEC>(src + off[k]);
+          if ((j + u) < n) v[u][k] = rows.load(p, c[u], k);
           else zero_vec(v[u][k]);
         }
       }
@@ -162,7 +208,7 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
   }
 }
 
-template <int VEC, int GROUP, int NACC>
+template <int VEC, int GROUP, int NACC, bool PARTS = false>
 __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
                                                  int batch_step, int gl, unsigned gmask,
                                                  typename VecT<VEC>::type (&acc)[NACC]) {
@@ -170,7 +216,7 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
   float s;
   load_col(p, beg + first_batch * GROUP, end, gl, c);
   load_scale(p, beg + first_batch * GROUP, end, gl, c, s);
-  accumulate_edges<VEC, GROUP, NACC>(p, beg, end, first_batch, batch_step, gl, gmask, acc, c, s);
+  accumulate_edges<VEC, GROUP, NACC, 0, PARTS>(p, beg, end, first_batch, batch_step, gl, gmask, acc, c, s);
 }
 
 // Scaled row result -> out (assign / += / red.add).
@@ -274,7 +320,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   grid_dependency_wait();
 }
 
-template <int VEC, int GROUP, int NACC>
+template <int VEC, int GROUP, int NACC, bool PARTS>
 __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
@@ -291,7 +337,7 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   T acc[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-  accumulate_edges<VEC, GROUP, NACC>(p, beg, end, 0, 1, gl, gmask, acc);
+  accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, 0, 1, gl, gmask, acc);
 
   const float r = p.rs ? __ldg(p.rs + row) : 1.f;
   write_row<VEC, GROUP, NACC>(p, row, gl, end > beg, r, acc);
@@ -306,7 +352,7 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
 // left most of the chip idle (the hub kernel cost as much as the main kernel on the config-4 stream).
 constexpr int kHubCluster = 8;
 
-template <int VEC, int GROUP, int NACC>
+template <int VEC, int GROUP, int NACC, bool PARTS>
 __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThreads)
     agg_hub_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
@@ -335,7 +381,7 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
     T acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-    accumulate_edges<VEC, GROUP, NACC>(p, beg, end, (crank * WARPS + wid) * GROUPS_PER_WARP + gidx,
+    accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, (crank * WARPS + wid) * GROUPS_PER_WARP + gidx,
                                        kHubCluster * WARPS * GROUPS_PER_WARP, gl, gmask, acc);
     // groups of one warp -> lanes [0, GROUP)
 #pragma unroll
@@ -414,7 +460,7 @@ cudaError_t launch_overlapped(void (*kernel)(KArgs...), int blocks, int threads,
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-template <int VEC, int GROUP, int NACC>
+template <int VEC, int GROUP, int NACC, bool PARTS>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
   const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
@@ -425,11 +471,11 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
   const bool overlap = hubs && p.num_edges >= (1 << 20);
   if (hubs) {
-    agg_hub_kernel<VEC, GROUP, NACC><<<(sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC, PARTS><<<(sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
-    if constexpr (GROUP == 32) {
+    if constexpr (GROUP == 32 && !PARTS) {
       // measured on config 5 (F=100 / 128): 3.48 / 3.34 ms against 3.99 / 3.88 ms for one row per warp;
       // 4 resident blocks per SM beat 3 (4.2 ms) and 2 (5.2 ms), 5..8 with a shorter unroll do not help.
       constexpr int kRowsPerWarp = 32;
@@ -441,26 +487,26 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
     } else {
       // narrow rows (several rows per warp): the lane groups of a warp diverge and the queue costs
       // more than it saves (F=64: 3.0 ms against 2.66 ms)
-      STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC>, blocks, kBlockThreads, stream, overlap, p));
+      STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC, PARTS>, blocks, kBlockThreads, stream, overlap, p));
     }
     STG_LAUNCH_CHECK("agg_rows_kernel");
   }
   return STG_OK;
 }
 
-template <int VEC>
+template <int VEC, bool PARTS>
 int dispatch_group(const AggParams& p, cudaStream_t stream, int avg_degree) {
   const int nvec = p.width / VEC;
   // (A 8-lane x 4-chunk geometry for short rows was measured for the halo-source pass: slower, 0.40 vs 0.28 ms.)
   (void)avg_degree;
-  if (nvec <= 1) return launch_agg<VEC, 1, 1>(p, stream);
-  if (nvec <= 2) return launch_agg<VEC, 2, 1>(p, stream);
-  if (nvec <= 4) return launch_agg<VEC, 4, 1>(p, stream);
-  if (nvec <= 8) return launch_agg<VEC, 8, 1>(p, stream);
-  if (nvec <= 16) return launch_agg<VEC, 16, 1>(p, stream);
-  if (nvec <= 32) return launch_agg<VEC, 32, 1>(p, stream);
-  if (nvec <= 64) return launch_agg<VEC, 32, 2>(p, stream);
-  return launch_agg<VEC, 32, 4>(p, stream);
+  if (nvec <= 1) return launch_agg<VEC, 1, 1, PARTS>(p, stream);
+  if (nvec <= 2) return launch_agg<VEC, 2, 1, PARTS>(p, stream);
+  if (nvec <= 4) return launch_agg<VEC, 4, 1, PARTS>(p, stream);
+  if (nvec <= 8) return launch_agg<VEC, 8, 1, PARTS>(p, stream);
+  if (nvec <= 16) return launch_agg<VEC, 16, 1, PARTS>(p, stream);
+  if (nvec <= 32) return launch_agg<VEC, 32, 1, PARTS>(p, stream);
+  if (nvec <= 64) return launch_agg<VEC, 32, 2, PARTS>(p, stream);
+  return launch_agg<VEC, 32, 4, PARTS>(p, stream);
 }
 
 }  // namespace
@@ -509,9 +555,15 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
     p.width = min(chunk, feat - f0);
     int rc;
     const int avg_degree = g->num_nodes > 0 ? g->num_edges / g->num_nodes : -1;
-    if (vec == 4) rc = dispatch_group<4>(p, stream, avg_degree);
-    else if (vec == 2) rc = dispatch_group<2>(p, stream, avg_degree);
-    else rc = dispatch_group<1>(p, stream, avg_degree);
+    if (nparts > 0) {
+      if (vec == 4) rc = dispatch_group<4, true>(p, stream, avg_degree);
+      else if (vec == 2) rc = dispatch_group<2, true>(p, stream, avg_degree);
+      else rc = dispatch_group<1, true>(p, stream, avg_degree);
+    } else {
+      if (vec == 4) rc = dispatch_group<4, false>(p, stream, avg_degree);
+      else if (vec == 2) rc = dispatch_group<2, false>(p, stream, avg_degree);
+      else rc = dispatch_group<1, false>(p, stream, avg_degree);
+    }
     if (rc != STG_OK) return rc;
   }
   return STG_OK;
