@@ -344,13 +344,33 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   grid_dependency_wait();
 }
 
-// Cluster per hub row: a thread-block cluster of kHubCluster CTAs (kHubCluster x 16 warps) owns one
-// hub row.  Every (CTA, warp, group) slot takes a strided share of the row's edge batches; partials are
-// reduced group->warp by shuffles, warp->CTA through shared memory, and CTA->cluster by the leader CTA
-// reading its peers' shared memory (DSMEM), each level in a fixed order: deterministic, no atomics, no
-// scratch buffer in HBM.  A power-law graph has a few rows with 10^4..10^5 edges; one CTA per such row
-// left most of the chip idle (the hub kernel cost as much as the main kernel on the config-4 stream).
+// Hub rows (longer than hub_threshold) in two tiers.  The hub list is walked in chunks of kHubCluster
+// entries by thread-block clusters of kHubCluster CTAs (16 warps each):
+//   * a row of up to kClusterRowEdges edges is summed by ONE CTA (entry q of the chunk by CTA q), so a
+//     cluster works on kHubCluster medium rows at once with no cluster-wide synchronisation;
+//   * a longer row (10^4..10^5 edges on a power-law graph) is summed by the whole cluster: every
+//     (CTA, warp, group) slot takes a strided share of the edge batches and the leader CTA adds the CTA
+//     sums through distributed shared memory.
+// Partials are reduced group->warp by shuffles, warp->CTA through shared memory, CTA->cluster over DSMEM,
+// each level in a fixed order: deterministic, no atomics, no scratch buffer in HBM.  (One cluster per row
+// for every hub row cost 10 us of latency chain + two cluster barriers per row: 0.66 ms for the 1077 hub
+// rows of config 5; one CTA per row for every hub row leaves the chip idle behind a 10^5-edge row.)
 constexpr int kHubCluster = 8;
+constexpr int kClusterRowEdges = 8192;
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor_vec(T v, int o);
+template <>
+__device__ __forceinline__ float shfl_xor_vec<float>(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <>
+__device__ __forceinline__ float2 shfl_xor_vec<float2>(float2 v, int o) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+template <>
+__device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
+                     __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
+}
 
 template <int VEC, int GROUP, int NACC, bool PARTS>
 __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThreads)
@@ -365,6 +385,7 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
   constexpr int WARPS = kHubThreads / 32;
   __shared__ T partial[WARPS][GROUP * NACC];
   __shared__ T cta_sum[GROUP * NACC];
+  __shared__ int chunk_row[kHubCluster], chunk_beg[kHubCluster], chunk_end[kHubCluster];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int gl = lane & (GROUP - 1);
@@ -374,34 +395,18 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
   const int cluster_id = blockIdx.x / kHubCluster;
   const int n_clusters = gridDim.x / kHubCluster;
   const int n_hub = min(__ldg(p.hub_count), p.hub_capacity);
-  for (int i = cluster_id; i < n_hub; i += n_clusters) {
-    const int row = __ldg(p.hub_rows + i);
-    const int beg = __ldg(p.row_off + row);
-    const int end = __ldg(p.row_off + row + 1);
+
+  // Sum edges of [beg,end) over `slots` cooperating (warp, group) slots starting at `slot`, then reduce
+  // the CTA's partials into cta_sum (valid after the trailing __syncthreads()).
+  auto cta_partial_sum = [&](int beg, int end, int slot, int slots) {
     T acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-    accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, (crank * WARPS + wid) * GROUPS_PER_WARP + gidx,
-                                       kHubCluster * WARPS * GROUPS_PER_WARP, gl, gmask, acc);
-    // groups of one warp -> lanes [0, GROUP)
+    accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, slot, slots, gl, gmask, acc);
 #pragma unroll
-    for (int o = GROUP; o < 32; o <<= 1) {
+    for (int o = GROUP; o < 32; o <<= 1) {        // groups of one warp -> lanes [0, GROUP)
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        T other;
-        if constexpr (VEC == 1) {
-          other = __shfl_xor_sync(0xffffffffu, acc[k], o);
-        } else if constexpr (VEC == 2) {
-          other.x = __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-          other.y = __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-        } else {
-          other.x = __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-          other.y = __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-          other.z = __shfl_xor_sync(0xffffffffu, acc[k].z, o);
-          other.w = __shfl_xor_sync(0xffffffffu, acc[k].w, o);
-        }
-        add_vec(acc[k], other);
-      }
+      for (int k = 0; k < NACC; ++k) add_vec(acc[k], shfl_xor_vec<T>(acc[k], o));
     }
     if (lane < GROUP) {
 #pragma unroll
@@ -416,30 +421,61 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
         cta_sum[k * GROUP + lane] = sum;
       }
     }
-    cluster.sync();                               // every CTA's cta_sum is written
-    if (crank == 0 && wid == 0 && lane < GROUP) { // CTAs of the cluster, fixed order, over DSMEM
-      const float r = p.rs ? __ldg(p.rs + row) : 1.f;
-      float* dst = p.out + static_cast<size_t>(row) * p.ld;
+    __syncthreads();
+  };
+  auto write_hub_row = [&](int row, T (&sum)[NACC]) {   // warp 0, lanes [0, GROUP)
+    const float r = p.rs ? __ldg(p.rs + row) : 1.f;
+    write_row<VEC, GROUP, NACC>(p, row, lane, true, r, sum);
+  };
+
+  for (int chunk = cluster_id; chunk * kHubCluster < n_hub; chunk += n_clusters) {
+    if (threadIdx.x < kHubCluster) {
+      const int i = chunk * kHubCluster + threadIdx.x;
+      int row = -1, beg = 0, end = 0;
+      if (i < n_hub) {
+        row = __ldg(p.hub_rows + i);
+        beg = __ldg(p.row_off + row);
+        end = __ldg(p.row_off + row + 1);
+      }
+      chunk_row[threadIdx.x] = row;
+      chunk_beg[threadIdx.x] = beg;
+      chunk_end[threadIdx.x] = end;
+    }
+    __syncthreads();
+    // tier 1: this CTA's own entry of the chunk
+    {
+      const int row = chunk_row[crank], beg = chunk_beg[crank], end = chunk_end[crank];
+      if (row >= 0 && (end - beg) <= kClusterRowEdges) {
+        cta_partial_sum(beg, end, wid * GROUPS_PER_WARP + gidx, WARPS * GROUPS_PER_WARP);
+        if (wid == 0 && lane < GROUP) {
+          T sum[NACC];
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        T sum = cta_sum[k * GROUP + lane];
-        for (int c = 1; c < kHubCluster; ++c) {
-          const T* remote = cluster.map_shared_rank(cta_sum, c);
-          add_vec(sum, remote[k * GROUP + lane]);
-        }
-        const int o = (lane + k * GROUP) * VEC;
-        if (o < p.width) {
-          scale_vec(sum, r);
-          if (p.accumulate == 2) {
-            red_add(dst + o, sum);
-            continue;
-          }
-          if (p.accumulate) add_vec(sum, *reinterpret_cast<const T*>(dst + o));
-          st_row<VEC>(dst + o, sum);
+          for (int k = 0; k < NACC; ++k) sum[k] = cta_sum[k * GROUP + lane];
+          write_hub_row(row, sum);
         }
       }
     }
-    cluster.sync();                               // peers keep cta_sum alive until the leader has read it
+    // tier 2: entries too long for one CTA, by the whole cluster (same decision in every CTA)
+    for (int q = 0; q < kHubCluster; ++q) {
+      const int row = chunk_row[q], beg = chunk_beg[q], end = chunk_end[q];
+      if (row < 0 || (end - beg) <= kClusterRowEdges) continue;
+      cta_partial_sum(beg, end, (crank * WARPS + wid) * GROUPS_PER_WARP + gidx, kHubCluster * WARPS * GROUPS_PER_WARP);
+      cluster.sync();                               // every CTA's cta_sum is written
+      if (crank == 0 && wid == 0 && lane < GROUP) { // CTAs of the cluster, fixed order, over DSMEM
+        T sum[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          sum[k] = cta_sum[k * GROUP + lane];
+          for (int c = 1; c < kHubCluster; ++c) {
+            const T* remote = cluster.map_shared_rank(cta_sum, c);
+            add_vec(sum[k], remote[k * GROUP + lane]);
+          }
+        }
+        write_hub_row(row, sum);
+      }
+      cluster.sync();                               // peers keep cta_sum alive until the leader has read it
+    }
+    __syncthreads();                                // chunk_* are rewritten by the next iteration
   }
 }
 
@@ -471,7 +507,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
   const bool overlap = hubs && p.num_edges >= (1 << 20);
   if (hubs) {
-    agg_hub_kernel<VEC, GROUP, NACC, PARTS><<<(sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC, PARTS><<<2 * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
