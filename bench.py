@@ -250,8 +250,12 @@ def main():
             out_f = torch.empty(hf.n_rows, FEAT, device=dev)
             out_b = torch.empty(hb.n_rows, FEAT, device=dev)
             push_blocks = int(os.environ.get("STG_PUSH_BLOCKS", "32"))
-            halo_info = {"mode": "halo rows pushed over NVLink by our kernel (posted stores into symmetric memory), "
-                                 "halo pass concurrent with the own-source pass (vector red.add); no NCCL on the data path",
+            push_flow = os.environ.get("STG_PUSH_FLOW", "serial")
+            halo_info = {"mode": "halo rows pushed over NVLink by our kernel (posted stores into symmetric memory) during the "
+                                 "own-source pass; " + ("halo-source pass += over the rows with remote neighbours"
+                                                        if push_flow == "serial" else
+                                                        "halo pass concurrent with the own-source pass (vector red.add)")
+                                 + "; no NCCL on the data path", "flow": push_flow,
                          "halo_rows_fwd": hf.n_halo, "halo_rows_bwd": hb.n_halo, "own_rows": hf.n_own,
                          "full_allgather_rows": n - hf.n_own, "halo_edges_fwd": int(hf.halo_cols.shape[0]),
                          "own_edges_fwd": int(hf.own_cols.shape[0]), "push_blocks": push_blocks}
@@ -260,10 +264,10 @@ def main():
             def step(ev=None):
                 if ev:
                     ev[0].record()
-                hf.aggregate_push(kernels, x_own, ns_own, nsh_f, rs_f, out_f, push_blocks=push_blocks)
+                hf.aggregate_push(kernels, x_own, ns_own, nsh_f, rs_f, out_f, push_blocks=push_blocks, flow=push_flow)
                 if ev:
                     ev[1].record()
-                hb.aggregate_push(kernels, g_own, ns_own, nsh_b, rs_b, out_b, push_blocks=push_blocks)
+                hb.aggregate_push(kernels, g_own, ns_own, nsh_b, rs_b, out_b, push_blocks=push_blocks, flow=push_flow)
         elif peer_ok and dist_mode == "pull":
             hf, hb = pg.halo_plans()
             own_lo, own_hi = hf.own_lo, hf.own_hi
@@ -379,6 +383,18 @@ def main():
         if rank == 0:
             for r_, s_ in enumerate(allsum):
                 print(f"[bench] rank {r_} aggregate_pull segments (ms): " + json.dumps({k: round(v, 3) for k, v in s_.items()}),
+                      file=sys.stderr)
+    if world > 1 and os.environ.get("STG_DIST_PROFILE") and dist_mode == "push":
+        hf.push_profile = []
+        for _ in range(6):
+            hf.aggregate_push(kernels, x_own, ns_own, nsh_f, rs_f, out_f, push_blocks=push_blocks, flow=push_flow)
+        summ = hf.push_profile_summary()
+        hf.push_profile = None
+        allsum = [None] * world
+        dist.all_gather_object(allsum, summ)
+        if rank == 0:
+            for r_, s_ in enumerate(allsum):
+                print(f"[bench] rank {r_} aggregate_push segments (ms): " + json.dumps({k: round(v, 3) for k, v in s_.items()}),
                       file=sys.stderr)
     ms_total = t_beg.elapsed_time(t_end)
     ms_fwd_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps

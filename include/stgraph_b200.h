@@ -93,6 +93,15 @@ int stg_agg_scaled_sum_accum_f32(const StgCsrView* g, const float* x, int32_t fe
 int stg_agg_scaled_sum_red_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,
                                const float* edge_scale, const float* row_scale, float* out, void* stream);
 
+/* Row-subset form: the view holds only a SUBSET of the output rows (view row i is output row out_rows[i];
+ * out_rows strictly increasing).  out[out_rows[i],:] (=, +=, red.add= for accumulate 0, 1, 2)
+ * row_scale[out_rows[i]] * sum over view row i.  The multi-GPU halo-source pass uses it with
+ * accumulate = 1: only the rows that have at least one remote neighbour are walked, after the
+ * own-source pass has written every row. */
+int stg_agg_scaled_sum_rows_f32(const StgCsrView* g, const int32_t* out_rows, const float* x, int32_t feat,
+                                const float* nbr_scale, const float* edge_scale, const float* row_scale, float* out,
+                                int32_t accumulate, void* stream);
+
 /* Same operation with the source matrix ROW-PARTITIONED into num_parts blocks (multi-GPU): block q holds
  * rows [part_bounds[q], part_bounds[q+1]) of x and may live in a peer GPU's memory mapped into this
  * process (CUDA IPC / symmetric memory): the kernel then fetches remote neighbour rows with NVLink

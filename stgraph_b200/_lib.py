@@ -13,7 +13,7 @@ import subprocess
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstgraph_b200.so")
+LIB_PATH = os.environ.get("STG_B200_LIB") or os.path.join(_HERE, "lib", "libstgraph_b200.so")   # env: A/B builds only
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 VM_MAX_TENSORS = 24
@@ -86,6 +86,8 @@ _SIGNATURES = {
                                                     c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_red_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_void_p], True),
+    "stg_agg_scaled_sum_rows_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_int32, c_void_p], True),
     "stg_halo_push_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, _P(c_void_p), c_int32,
                                          c_int32, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,

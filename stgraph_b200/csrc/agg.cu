@@ -48,6 +48,7 @@ struct AggParams {
   const int32_t* __restrict__ eids;
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ hub_count;
+  const int32_t* __restrict__ out_rows;   // view row -> output row (NULL: identity)
   int num_rows;
   int num_edges;
   int eid_base;
@@ -152,23 +153,53 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
   constexpr int UNROLL = UNROLL_ > 0 ? (UNROLL_ < GROUP ? UNROLL_ : GROUP) : (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
   const RowLoader<VEC, GROUP, NACC, PARTS> rows(p, gl);
 
+  // (column, scale) of the batch a lane group is summing reach the other lanes either by two SHFL per edge
+  // or through shared memory (one STS.64 per lane + one LDS.128 per TWO edges).  A/B on one box, config 5:
+  // sub-warp groups (F=64, GROUP=16) 2.04 ms through shared memory against 2.34 ms with shuffles; full-warp
+  // groups (F=100 / 128) 2.92 / 3.07 ms against 2.79 / 2.82 ms -- so each geometry takes its winner.
+  constexpr bool kSmemMeta = GROUP < 32;
+  __shared__ int2 meta[kSmemMeta ? kHubThreads : 1];
+  const int2* gmeta = meta + (threadIdx.x & ~(GROUP - 1));
+  auto fetch_meta = [&](int j, int (&c)[UNROLL], float (&sc)[UNROLL]) {
+    if constexpr (!kSmemMeta) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        c[u] = __shfl_sync(gmask, my_c, j + u, GROUP);
+        sc[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
+      }
+    } else if constexpr (UNROLL == 1) {
+      c[0] = gmeta[j].x;
+      sc[0] = __int_as_float(gmeta[j].y);
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u += 2) {
+        const int4 m = *reinterpret_cast<const int4*>(gmeta + j + u);
+        c[u] = m.x;
+        sc[u] = __int_as_float(m.y);
+        c[u + 1] = m.z;
+        sc[u + 1] = __int_as_float(m.w);
+      }
+    }
+  };
+
   int base = beg + first_batch * GROUP;
   int nx_c;
   float nx_s;
   for (; base < end; base += batch_step * GROUP) {
+    if constexpr (kSmemMeta) {
+      __syncwarp(gmask);                                     // the previous batch has been read by every lane
+      meta[threadIdx.x] = make_int2(my_c, __float_as_int(my_s));
+      __syncwarp(gmask);
+    }
     load_col(p, base + batch_step * GROUP, end, gl, nx_c);   // prefetch next batch
     load_scale(p, base + batch_step * GROUP, end, gl, nx_c, nx_s);
     const int n = min(GROUP, end - base);
     int j = 0;
     for (; j + UNROLL <= n; j += UNROLL) {     // full groups: UNROLL unpredicated row loads in flight
       int c[UNROLL];
-      float s[UNROLL];
+      float sc[UNROLL];
       T v[UNROLL][NACC];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        c[u] = __shfl_sync(gmask, my_c, j + u, GROUP);
-        s[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
-      }
+      fetch_meta(j, c, sc);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -177,18 +208,14 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], s[u], v[u][k]);
+        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], sc[u], v[u][k]);
       }
     }
     if (j < n) {                               // last, partial group of the batch
       int c[UNROLL];
-      float s[UNROLL];
+      float sc[UNROLL];
       T v[UNROLL][NACC];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        c[u] = __shfl_sync(gmask, my_c, j + u, GROUP);
-        s[u] = __shfl_sync(gmask, my_s, j + u, GROUP);
-      }
+      fetch_meta(j, c, sc);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -200,7 +227,7 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], s[u], v[u][k]);
+        for (int k = 0; k < NACC; ++k) fma_vec(acc[k], sc[u], v[u][k]);
       }
     }
     my_c = nx_c;
@@ -267,13 +294,16 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
     if (lane == 0) s = atomicAdd(&next_slot, 1);
     return __shfl_sync(0xffffffffu, s, 0);
   };
-  // stage A: slot -> row, [beg, end); row = -1 when there is nothing to do (past the end, hub row)
+  // stage A: slot -> output row, [beg, end); end = -1 when there is nothing to do (past the end, hub row)
   auto stage_a = [&](int slot, int& row, int& beg, int& end) {
     row = slot * GPW + gidx;
-    beg = end = 0;
-    if (slot >= last || row >= p.num_rows) { row = -1; return; }
+    if (slot >= last || row >= p.num_rows) { row = 0; beg = 0; end = -1; return; }
     beg = __ldg(p.row_off + row);
     end = __ldg(p.row_off + row + 1);
+    if (p.out_rows) row = __ldg(p.out_rows + row);
+  };
+  auto drop_hub = [&](int& beg, int& end) {
+    if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) beg = 0, end = -1;
   };
 
   int slot0, row0, beg0, end0, c0;     // row being summed (scale loaded at the top of the iteration)
@@ -287,26 +317,26 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   stage_a(slot1, row1, beg1, end1);
   int slot2 = draw();
   stage_a(slot2, row2, beg2, end2);
-  if (row0 >= 0 && p.hub_threshold > 0 && (end0 - beg0) > p.hub_threshold) row0 = -1, end0 = beg0;
+  drop_hub(beg0, end0);
   load_col(p, beg0, end0, gl, c0);
-  if (row1 >= 0 && p.hub_threshold > 0 && (end1 - beg1) > p.hub_threshold) row1 = -1, end1 = beg1;
+  drop_hub(beg1, end1);
   load_col(p, beg1, end1, gl, c1);
   load_scale(p, beg0, end0, gl, c0, s0);
-  r0 = (row0 >= 0 && p.rs) ? __ldg(p.rs + row0) : 1.f;
+  r0 = (end0 >= 0 && p.rs) ? __ldg(p.rs + row0) : 1.f;
 
   while (slot0 < last) {
     // issue the loads of the three younger stages before touching the current row
     const int slot3 = draw();
     int row3, beg3, end3;
     stage_a(slot3, row3, beg3, end3);
-    if (row2 >= 0 && p.hub_threshold > 0 && (end2 - beg2) > p.hub_threshold) row2 = -1, end2 = beg2;
+    drop_hub(beg2, end2);
     int c2;
     load_col(p, beg2, end2, gl, c2);
     float s1;
     load_scale(p, beg1, end1, gl, c1, s1);
-    const float r1 = (row1 >= 0 && p.rs) ? __ldg(p.rs + row1) : 1.f;
+    const float r1 = (end1 >= 0 && p.rs) ? __ldg(p.rs + row1) : 1.f;
 
-    if (row0 >= 0) {
+    if (end0 >= 0) {
       T acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
@@ -339,8 +369,9 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
   accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, 0, 1, gl, gmask, acc);
 
-  const float r = p.rs ? __ldg(p.rs + row) : 1.f;
-  write_row<VEC, GROUP, NACC>(p, row, gl, end > beg, r, acc);
+  const int orow = p.out_rows ? __ldg(p.out_rows + row) : row;
+  const float r = p.rs ? __ldg(p.rs + orow) : 1.f;
+  write_row<VEC, GROUP, NACC>(p, orow, gl, end > beg, r, acc);
   grid_dependency_wait();
 }
 
@@ -424,8 +455,9 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
     __syncthreads();
   };
   auto write_hub_row = [&](int row, T (&sum)[NACC]) {   // warp 0, lanes [0, GROUP)
-    const float r = p.rs ? __ldg(p.rs + row) : 1.f;
-    write_row<VEC, GROUP, NACC>(p, row, lane, true, r, sum);
+    const int orow = p.out_rows ? __ldg(p.out_rows + row) : row;
+    const float r = p.rs ? __ldg(p.rs + orow) : 1.f;
+    write_row<VEC, GROUP, NACC>(p, orow, lane, true, r, sum);
   };
 
   for (int chunk = cluster_id; chunk * kHubCluster < n_hub; chunk += n_clusters) {
@@ -550,8 +582,9 @@ int dispatch_group(const AggParams& p, cudaStream_t stream, int avg_degree) {
 int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, const float* ns,
                           const float* es, const float* rs, float* out, cudaStream_t stream,
                           int nparts = 0, const float* const* parts = nullptr, const int32_t* bounds = nullptr,
-                          int accumulate = 0) {
+                          int accumulate = 0, const int32_t* out_rows = nullptr) {
   AggParams p;
+  p.out_rows = out_rows;
   p.accumulate = accumulate;
   p.nparts = nparts;
   for (int q = 0; q < STG_MAX_PARTS; ++q) p.xs[q] = q < nparts ? parts[q] : nullptr;
@@ -694,6 +727,21 @@ STG_API int stg_agg_scaled_sum_accum_f32(const StgCsrView* g, const float* x, in
   STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
   STG_CHECK_ARG(x != out, "x and out must not alias");
   return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream), 0, nullptr, nullptr, 1);
+}
+
+STG_API int stg_agg_scaled_sum_rows_f32(const StgCsrView* g, const int32_t* out_rows, const float* x, int32_t feat,
+                                        const float* nbr_scale, const float* edge_scale, const float* row_scale,
+                                        float* out, int32_t accumulate, void* stream) {
+  int rc = validate_view(g, edge_scale != nullptr);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  STG_CHECK_ARG(accumulate >= 0 && accumulate <= 2, "accumulate must be 0, 1 or 2 (got %d)", accumulate);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(out_rows != nullptr, "out_rows is NULL");
+  STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
+  STG_CHECK_ARG(x != out, "x and out must not alias");
+  return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream), 0, nullptr, nullptr,
+                               accumulate, out_rows);
 }
 
 STG_API int stg_agg_scaled_sum_red_f32(const StgCsrView* g, const float* x, int32_t feat, const float* nbr_scale,

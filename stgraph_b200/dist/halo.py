@@ -58,6 +58,13 @@ class HaloPlan:
 
         self.own_ro, self.own_cols, self.own_eids = sub_csr(local, cols - self.own_lo)
         self.halo_ro, self.halo_cols, self.halo_eids = sub_csr(~local, torch.searchsorted(self.halo_ids, cols.contiguous()))
+        # the halo-source edges once more, over ONLY the rows that have any (view row i = local row halo_out_rows[i])
+        hdeg = (self.halo_ro[1:] - self.halo_ro[:-1])
+        sel = torch.nonzero(hdeg > 0).reshape(-1)
+        self.halo_out_rows = sel.to(torch.int32).contiguous()
+        cro = torch.zeros(sel.numel() + 1, dtype=torch.int32, device=dev)
+        cro[1:] = torch.cumsum(hdeg[sel].to(torch.int64), 0).to(torch.int32)
+        self.halo_compact_ro = cro.contiguous()
         self.eid_base = csr.eid_base
         self.num_global_edges = csr.num_edges
         self.num_local_edges = e1 - e0
@@ -78,13 +85,14 @@ class HaloPlan:
         self._keep = []
 
     # ------------------------------------------------------- overlapped two-pass form
-    def _make_view(self, ro, cols, eids):
+    def _make_view(self, ro, cols, eids, n_rows=None):
         dev = ro.device
+        n_rows = self.n_rows if n_rows is None else n_rows
         n_e = int(cols.shape[0])
         cap = n_e // max(HUB_THRESHOLD, 1) + 1
         hub_rows = torch.empty(cap, dtype=torch.int32, device=dev)
         hub_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.call("stg_csr_hub_rows", ro.data_ptr(), self.n_rows, HUB_THRESHOLD, hub_rows.data_ptr(), cap,
+        _lib.call("stg_csr_hub_rows", ro.data_ptr(), n_rows, HUB_THRESHOLD, hub_rows.data_ptr(), cap,
                   hub_count.data_ptr(), _lib.current_stream_ptr())
         has_hubs = int(hub_count.item()) > 0
         self._keep.append((hub_rows, hub_count))
@@ -93,7 +101,7 @@ class HaloPlan:
         v.column_indices = cols.data_ptr() if n_e else None
         v.eids = eids.data_ptr() if n_e else None
         v.node_ids = None
-        v.num_nodes = self.n_rows
+        v.num_nodes = n_rows
         v.num_edges = n_e                  # edges of THIS sub-CSR (the kernel picks its row geometry from the mean degree)
         v.eid_base = self.eid_base
         v.eids_identity = 0
@@ -109,6 +117,13 @@ class HaloPlan:
             self._split_views = (self._make_view(self.own_ro, self.own_cols, self.own_eids),
                                  self._make_view(self.halo_ro, self.halo_cols, self.halo_eids))
         return self._split_views
+
+    def halo_compact_view(self):
+        """Halo-source edges over the rows that have any; pair with ``out_rows=self.halo_out_rows``."""
+        if getattr(self, "_compact_view", None) is None:
+            self._compact_view = self._make_view(self.halo_compact_ro, self.halo_cols, self.halo_eids,
+                                                 n_rows=int(self.halo_out_rows.numel()))
+        return self._compact_view
 
     def new_halo_buffer(self, feat: int, like: torch.Tensor) -> torch.Tensor:
         return torch.empty(max(self.n_halo, 1), feat, dtype=like.dtype, device=like.device)[:self.n_halo]
@@ -222,29 +237,96 @@ class HaloPlan:
     def halo_rows_view(self, k: int) -> torch.Tensor:
         return self._halo_symm[k * self._max_halo: k * self._max_halo + self.n_halo]
 
-    def aggregate_push(self, kernels, own, ns_own, ns_halo, rs, out, es=None, push_blocks=32):
-        """Two concurrent passes into a zero-filled ``out`` (vector red.add): the own-source pass on the
-        current stream; on a side stream the halo push (posted NVLink stores into the peers' symmetric halo
-        buffers), one device barrier, and the halo-source pass.  Double-buffered halo storage makes that
-        single barrier sufficient.  Each output element receives at most two addends -> deterministic."""
+    def aggregate_push(self, kernels, own, ns_own, ns_halo, rs, out, es=None, push_blocks=32, flow="serial"):
+        """Halo rows are pushed into the peers' symmetric halo buffers by ``stg_halo_push_f32`` (posted NVLink
+        stores, side stream) while the own-source pass runs; one device barrier; then the halo-source pass.
+        Double-buffered halo storage makes that single barrier sufficient.
+
+        ``flow="serial"`` (default): the own-source pass WRITES every row, the halo-source pass then ``+=`` over
+        only the rows that have a remote neighbour (compacted view, ``stg_agg_scaled_sum_rows_f32``) on the same
+        stream: no memset, no atomics, fixed order.  ``flow="concurrent"``: both passes ``red.add`` into a
+        zero-filled ``out`` on two streams (at most two addends per element -> still deterministic); measured
+        slower once the gather kernel became L2-bound, because concurrency no longer hides any work."""
+        if flow == "serial":
+            return self._aggregate_push_serial(kernels, own, ns_own, ns_halo, rs, out, es, push_blocks)
         k = self._iter & 1
         self._iter += 1
         v_own, v_halo = self.split_views()
         cur = torch.cuda.current_stream()
         side = self._side
+        prof = getattr(self, "push_profile", None)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)] if prof is not None else None
+        if ev:
+            ev[0].record(cur)
         out.zero_()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
+            if ev:
+                ev[2].record(side)
             _lib.call("stg_halo_push_f32", own.data_ptr(), self._feat, self.send_index.data_ptr(), self._send_peer.data_ptr(),
                       self._send_slot.data_ptr(), int(self.send_index.numel()), self._push_ptrs[k], self.world,
                       int(push_blocks), side.cuda_stream)
+            if ev:
+                ev[3].record(side)
             self._halo_hdl.barrier()                      # every rank's pushes for this step have landed
+            if ev:
+                ev[4].record(side)
             if self.n_halo > 0:
                 kernels.agg_scaled_sum(v_halo, self.halo_rows_view(k), ns_halo, es, rs, out=out, accumulate="red",
                                        stream=side.cuda_stream)
+            if ev:
+                ev[5].record(side)
+        if ev:
+            ev[1].record(cur)
         kernels.agg_scaled_sum(v_own, own, ns_own, es, rs, out=out, accumulate="red")
+        if ev:
+            ev[6].record(cur)
+            prof.append(ev)
         cur.wait_stream(side)
         return out
+
+    def _aggregate_push_serial(self, kernels, own, ns_own, ns_halo, rs, out, es, push_blocks):
+        k = self._iter & 1
+        self._iter += 1
+        v_own, _ = self.split_views()
+        cur = torch.cuda.current_stream()
+        side = self._side
+        prof = getattr(self, "push_profile", None)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)] if prof is not None else None
+        if ev:
+            ev[0].record(cur)
+            ev[1].record(cur)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if ev:
+                ev[2].record(side)
+            _lib.call("stg_halo_push_f32", own.data_ptr(), self._feat, self.send_index.data_ptr(), self._send_peer.data_ptr(),
+                      self._send_slot.data_ptr(), int(self.send_index.numel()), self._push_ptrs[k], self.world,
+                      int(push_blocks), side.cuda_stream)
+            if ev:
+                ev[3].record(side)
+            self._halo_hdl.barrier()                      # every rank's pushes for this step have landed
+            if ev:
+                ev[4].record(side)
+        kernels.agg_scaled_sum(v_own, own, ns_own, es, rs, out=out)
+        if ev:
+            ev[6].record(cur)
+        cur.wait_stream(side)
+        if self.n_halo > 0:
+            kernels.agg_scaled_sum(self.halo_compact_view(), self.halo_rows_view(k), ns_halo, es, rs, out=out,
+                                   accumulate=True, out_rows=self.halo_out_rows)
+        if ev:
+            ev[5].record(cur)
+            prof.append(ev)
+        return out
+
+    def push_profile_summary(self):
+        """Mean device time (ms) of the segments of aggregate_push (set ``plan.push_profile = []`` to collect)."""
+        torch.cuda.synchronize()
+        n = max(len(self.push_profile), 1)
+        seg = {"zero": (0, 1), "own_pass": (1, 6), "push": (2, 3), "barrier": (3, 4), "halo_pass_or_wait": (4, 5),
+               "own_end_to_halo_end": (6, 5), "start_to_halo_end": (0, 5)}
+        return {k: sum(e[a].elapsed_time(e[b]) for e in self.push_profile) / n for k, (a, b) in seg.items()}
 
     def profile_summary(self):
         """Mean device time (ms) of each segment of aggregate_pull (set ``plan.profile = []`` to collect)."""

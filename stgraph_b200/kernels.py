@@ -28,11 +28,21 @@ def _check(t: torch.Tensor, name: str, dtype=torch.float32):
 
 
 def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
-                   out: torch.Tensor | None = None, accumulate=False, stream=None) -> torch.Tensor:
-    """``out[r] = row_scale[r] * sum_e nbr_scale[c_e] * edge_scale[eid_e] * x[c_e]`` (see ``stg_agg_scaled_sum_f32``)."""
+                   out: torch.Tensor | None = None, accumulate=False, stream=None, out_rows=None) -> torch.Tensor:
+    """``out[r] = row_scale[r] * sum_e nbr_scale[c_e] * edge_scale[eid_e] * x[c_e]`` (see ``stg_agg_scaled_sum_f32``).
+
+    ``accumulate``: False (assign), True (``+=``) or ``"red"`` (``red.global.add``).  ``out_rows`` (int32, strictly
+    increasing): the view holds a subset of the output rows, view row ``i`` is ``out[out_rows[i]]``
+    (``stg_agg_scaled_sum_rows_f32``); ``out`` is then required.
+    """
     global launch_count
     _check(x, "x")
     n = view.num_nodes                      # rows of this view (a row slice of a partitioned graph has fewer rows than x)
+    if out_rows is not None:
+        _check(out_rows, "out_rows", torch.int32)
+        if out is None or out_rows.numel() != n:
+            raise ValueError("out_rows needs out= and one entry per view row")
+        n = out.shape[0]
     if x.dim() < 2:
         raise ValueError("x must be [rows, feat...]")
     feat = x.numel() // max(x.shape[0], 1)
@@ -55,7 +65,13 @@ def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_
         _check(out, "out")
         if out.shape[0] != n or out.numel() != n * feat:
             raise ValueError(f"out must be [{n}, {feat}], got {tuple(out.shape)}")
-    if n == 0 or feat == 0:
+    if n == 0 or feat == 0 or view.num_nodes == 0:
+        return out
+    if out_rows is not None:
+        _lib.call("stg_agg_scaled_sum_rows_f32", ctypes.byref(view), out_rows.data_ptr(), x.data_ptr(), feat,
+                  _lib.ptr(nbr_scale), _lib.ptr(edge_scale), _lib.ptr(row_scale), out.data_ptr(),
+                  {False: 0, True: 1, "red": 2}[accumulate], stream if stream is not None else _lib.current_stream_ptr())
+        launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
         return out
     fn = {False: "stg_agg_scaled_sum_f32", True: "stg_agg_scaled_sum_accum_f32", "red": "stg_agg_scaled_sum_red_f32"}[accumulate]
     _lib.call(fn, ctypes.byref(view), x.data_ptr(), feat, _lib.ptr(nbr_scale), _lib.ptr(edge_scale), _lib.ptr(row_scale),

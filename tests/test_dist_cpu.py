@@ -128,6 +128,17 @@ def _halo_worker(rank, world, port, n, src, dst, x, ret):
                                          edge_scale=w, dtype=torch.float64)
             assert torch.allclose(two, local, rtol=1e-5, atol=1e-6)
             assert int(plan.own_cols.shape[0]) + int(plan.halo_cols.shape[0]) == plan.num_local_edges
+            # compacted halo view: only rows with a remote neighbour, same edges, rows strictly increasing
+            hdeg = plan.halo_ro[1:] - plan.halo_ro[:-1]
+            assert torch.equal(plan.halo_out_rows.long(), torch.nonzero(hdeg > 0).reshape(-1))
+            cdeg = plan.halo_compact_ro[1:] - plan.halo_compact_ro[:-1]
+            assert torch.equal(cdeg, hdeg[plan.halo_out_rows.long()]) and int(plan.halo_compact_ro[-1]) == plan.halo_cols.shape[0]
+            if plan.n_halo:
+                comp = A.scaled_sum(plan.halo_compact_ro.numpy(), plan.halo_cols.numpy(), plan.halo_eids.numpy(), halo,
+                                    edge_scale=w, dtype=torch.float64)
+                wide = A.scaled_sum(plan.halo_ro.numpy(), plan.halo_cols.numpy(), plan.halo_eids.numpy(), halo,
+                                    edge_scale=w, dtype=torch.float64)
+                assert torch.equal(comp, wide[plan.halo_out_rows.long()])
             res[tag] = (plan.row_lo, plan.row_hi, local, plan.n_halo)
         ret[rank] = res
     finally:

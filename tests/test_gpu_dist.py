@@ -118,3 +118,64 @@ def test_two_concurrent_red_passes_are_deterministic_and_correct(cuda):
     out = kernels.agg_scaled_sum(va, x, norm, None, norm)
     kernels.agg_scaled_sum(vb, x, norm, None, norm, out=out, accumulate=True)
     assert torch.equal(out, results[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("feat", [100, 16, 192])
+def test_row_subset_pass_accumulates_into_the_mapped_rows(cuda, feat):
+    """stg_agg_scaled_sum_rows_f32: own-source pass writes all rows, the compacted second pass += only its rows."""
+    from stgraph_b200 import _lib, kernels
+    from stgraph_b200.graph import StaticGraph
+    from stgraph_b200.utils import synthetic
+
+    n = 20000
+    src, dst = synthetic.power_law_graph(n, 400000, alpha=2.1, locality=0.5, window=512, max_degree=5000, seed=3, device=cuda)
+    g = StaticGraph(torch.stack([src, dst], 1), None, n)
+    F_ = g._forward_graph
+    norm = g.degree_norm().reshape(-1).contiguous()
+    x = torch.randn(n, feat, device=cuda)
+    full = kernels.agg_scaled_sum(g.fwd_view(), x, norm, None, norm)
+    mag = kernels.agg_scaled_sum(g.fwd_view(), x.abs(), norm, None, norm)
+    ro = F_.row_offset.long()
+    deg = ro[1:] - ro[:-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=cuda), deg)
+    second = (F_.column_indices.long() % 7) == 0          # "remote" sources: a sparse subset of the edges, hub rows included
+    keep = []
+
+    def view(ro32, cols, n_rows, hub=False):
+        v = _lib.StgCsrView()
+        v.row_offset, v.column_indices, v.eids, v.node_ids = ro32.data_ptr(), cols.data_ptr(), None, None
+        v.num_nodes, v.num_edges, v.eid_base, v.eids_identity = n_rows, int(cols.shape[0]), 0, 1
+        v.hub_rows = v.hub_count = None
+        v.hub_threshold = v.hub_capacity = 0
+        if hub:
+            cap = int(cols.shape[0]) // 64 + 1
+            hr = torch.empty(cap, dtype=torch.int32, device=cuda)
+            hc = torch.zeros(1, dtype=torch.int32, device=cuda)
+            _lib.call("stg_csr_hub_rows", ro32.data_ptr(), n_rows, 64, hr.data_ptr(), cap, hc.data_ptr(), _lib.current_stream_ptr())
+            assert int(hc.item()) > 0
+            keep.append((hr, hc))
+            v.hub_rows, v.hub_count, v.hub_threshold, v.hub_capacity = hr.data_ptr(), hc.data_ptr(), 64, cap
+        keep.append((ro32, cols))
+        return v
+
+    cnt1 = torch.bincount(rows[~second], minlength=n)
+    ro1 = torch.zeros(n + 1, dtype=torch.int32, device=cuda)
+    ro1[1:] = torch.cumsum(cnt1, 0).int()
+    cnt2 = torch.bincount(rows[second], minlength=n)
+    sel = torch.nonzero(cnt2 > 0).reshape(-1)
+    assert 0 < sel.numel() < n
+    ro2 = torch.zeros(sel.numel() + 1, dtype=torch.int32, device=cuda)
+    ro2[1:] = torch.cumsum(cnt2[sel], 0).int()
+    v1 = view(ro1, F_.column_indices[~second].contiguous(), n)
+    for hub in (False, True):
+        v2 = view(ro2, F_.column_indices[second].contiguous(), int(sel.numel()), hub=hub)
+        out = kernels.agg_scaled_sum(v1, x, norm, None, norm)
+        kernels.agg_scaled_sum(v2, x, norm, None, norm, out=out, accumulate=True, out_rows=sel.int().contiguous())
+        assert bool(((out - full).abs() <= 2e-6 * mag + 1e-30).all())
+        # assign form touches only the mapped rows
+        out2 = torch.full((n, feat), 7.0, device=cuda)
+        kernels.agg_scaled_sum(v2, x, norm, None, norm, out=out2, out_rows=sel.int().contiguous())
+        untouched = torch.ones(n, dtype=torch.bool, device=cuda)
+        untouched[sel] = False
+        assert bool((out2[untouched] == 7.0).all()) and bool((out2[sel] != 7.0).any())
