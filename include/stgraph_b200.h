@@ -80,6 +80,33 @@ int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t feat,
                            const float* nbr_scale, const float* edge_scale,
                            const float* row_scale, float* out, void* stream);
 
+/* Packed edge metadata: one {column, scale} pair per CSR slot, in CSR order, with
+ * scale = nbr_scale[column] * edge_scale[eid].  The aggregation then issues ONE coalesced 8-byte load per
+ * edge instead of a column load followed by dependent scattered 4-byte gathers (one 32-byte L2 sector
+ * request per edge).  For a static graph with a fixed norm (GCNConv: stgraph/nn/pytorch/static/
+ * gcn_conv.py:162-182 reads the same g.ndata["norm"] every call) the packing is paid once per graph. */
+typedef struct StgEdgeMeta {
+  int32_t col;
+  float scale;
+} StgEdgeMeta;
+
+/* meta[e] = {column_indices[e], nbr_scale[column_indices[e]] * edge_scale[eid(e)]} for every slot e of the
+ * view's CSR arrays (either scale may be NULL = 1).  meta: [num_edges] device array, 8-byte aligned. */
+int stg_csr_pack_edge_meta_f32(const StgCsrView* g, const float* nbr_scale, const float* edge_scale,
+                               StgEdgeMeta* meta, void* stream);
+
+/* out[r,:] (=, +=, red.add= for accumulate 0, 1, 2) row_scale[r] * sum_{e in row r} meta[e].scale * x[meta[e].col,:]
+ * -- the same sums, bit for bit, as stg_agg_scaled_sum_f32 with the scales meta was packed from. */
+int stg_agg_packed_sum_f32(const StgCsrView* g, const StgEdgeMeta* meta, const float* x, int32_t feat,
+                           const float* row_scale, float* out, int32_t accumulate, void* stream);
+
+/* The same with explicit row strides (in floats, >= feat) for x and out, so that column blocks of a wider
+ * buffer (e.g. one gate of the fused TGCN cell's [N, 3H] tensor) or row-padded buffers are aggregated in place.
+ * (Padding F=100 rows to 512-byte lines was measured: no faster -- the gather is not bound by line alignment.) */
+int stg_agg_packed_sum_strided_f32(const StgCsrView* g, const StgEdgeMeta* meta, const float* x, int32_t feat,
+                                   int32_t x_ld, const float* row_scale, float* out, int32_t out_ld,
+                                   int32_t accumulate, void* stream);
+
 /* Accumulating form: out[r,:] += row_scale[r] * sum(...).  Used when a row's edge set is split in two CSRs
  * (edges to locally owned sources / edges to halo sources) so that the first pass overlaps the halo
  * exchange; the passes run in a fixed order, so the result stays deterministic. */

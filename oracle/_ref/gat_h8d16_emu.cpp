@@ -23,18 +23,18 @@ extern "C" void K4
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V22_tmp = 0;
-            int offset0 = dst_id * 8 + tx;
+            int offset1 = dst_id * 8 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset1 = src_id * 8 + tx;int offset2 = eid * 8 + tx;
+                int offset0 = src_id * 8 + tx;int offset2 = eid * 8 + tx;
                 
                 
                 
-                float V18_tmp = Velinb[offset1] + Vercen[offset0];
+                float V18_tmp = Velinb[offset0] + Vercen[offset1];
                 
                 
                 
@@ -57,7 +57,7 @@ extern "C" void K4
             }
             
             
-            V22[offset0] = V22_tmp;
+            V22[offset1] = V22_tmp;
             
             
             

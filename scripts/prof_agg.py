@@ -12,6 +12,10 @@ n = d['num_nodes']
 g = StaticGraph(torch.stack([d['src'], d['dst']], 1), None, n)
 norm = g.degree_norm().reshape(-1)
 x = torch.randn(n, F, device=dev); out = torch.empty_like(x)
+plain = len(sys.argv) > 3 and sys.argv[3] == 'plain'
 for _ in range(4):
-    kernels.agg_scaled_sum(g.fwd_view(), x, norm, None, norm, out=out)
+    if plain:
+        kernels.agg_scaled_sum(g.fwd_view(), x, norm, None, norm, out=out)
+    else:   # packed {col, scale} metadata (what a static graph runs; the pack kernel is launch 0)
+        kernels.agg_scaled_sum_graph(g._forward_graph, x, norm, None, norm, out=out)
 torch.cuda.synchronize()

@@ -88,6 +88,11 @@ _SIGNATURES = {
                                                   c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_rows_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                                    c_void_p, c_int32, c_void_p], True),
+    "stg_csr_pack_edge_meta_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_void_p], True),
+    "stg_agg_packed_sum_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+                                              c_void_p], True),
+    "stg_agg_packed_sum_strided_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                                      c_void_p, c_int32, c_int32, c_void_p], True),
     "stg_halo_push_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, _P(c_void_p), c_int32,
                                          c_int32, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,

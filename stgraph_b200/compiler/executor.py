@@ -209,8 +209,13 @@ class Executor:
         if la.kind == "scaled_sum":
             get = lambda v: None if v is None else tensor_map[v.id].detach()
             flat = lambda t: None if t is None else t.reshape(-1)
-            kernels.agg_scaled_sum(view, get(la.x), flat(get(la.ns)), flat(get(la.es)), flat(get(la.rs)),
-                                   out=tensor_map[la.out.id])
+            csr = graph._forward_graph if la.center == ValType.DEST else graph._backward_graph
+            if getattr(csr, "pack_enabled", False):     # static graph: packed {col, scale} array, built on first use
+                kernels.agg_scaled_sum_graph(csr, get(la.x), flat(get(la.ns)), flat(get(la.es)), flat(get(la.rs)),
+                                             out=tensor_map[la.out.id])
+            else:
+                kernels.agg_scaled_sum(view, get(la.x), flat(get(la.ns)), flat(get(la.es)), flat(get(la.rs)),
+                                       out=tensor_map[la.out.id])
             return
         ptrs = (ctypes.c_void_p * _lib.VM_MAX_TENSORS)()
         for i, v in enumerate(la.tensor_vars):

@@ -25,6 +25,9 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace stg {
 namespace {
 
@@ -49,6 +52,7 @@ struct AggParams {
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ hub_count;
   const int32_t* __restrict__ out_rows;   // view row -> output row (NULL: identity)
+  const int2* __restrict__ meta;          // PACKED mode: {column, scale bits} of every CSR slot (stg_csr_pack_edge_meta_f32)
   int num_rows;
   int num_edges;
   int eid_base;
@@ -57,7 +61,8 @@ struct AggParams {
   int hub_capacity;
   const float* __restrict__ x;    // already offset to the chunk's first column
   float* __restrict__ out;        // same
-  int ld;                         // floats between consecutive rows (= feat)
+  int ld;                         // floats between consecutive rows of x (>= feat)
+  int ld_out;                     // floats between consecutive rows of out (>= feat)
   int width;                      // floats of this chunk handled by the launch
   const float* __restrict__ ns;
   const float* __restrict__ es;
@@ -88,13 +93,38 @@ __device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
 // complete" implies "hub rows written" for whatever follows in the stream.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Column index and combined scale of edge `base + gl` (0 / 0.f past the end of the row).
-__device__ __forceinline__ void load_col(const AggParams& p, int base, int end, int gl, int& c) {
+// How the edge loop finds a neighbour row and its scale:
+//   kPlain   column_indices[e], then the dependent gathers nbr_scale[col] (* edge_scale[eid]);
+//   kParts   as kPlain, source matrix row-partitioned over peer GPUs (cold path, stg_agg_scaled_sum_parts_f32);
+//   kPacked  ONE coalesced 8-byte load per edge: {col, nbr_scale[col] * edge_scale[eid]} precomputed per CSR slot
+//            (stg_csr_pack_edge_meta_f32).  The scattered 4-byte nbr_scale gather costs one 32-byte L2 sector
+//            request per edge -- as many requests as a quarter of the 400..512-byte neighbour row itself -- and
+//            one level of the dependent load chain; a static graph with a fixed norm pays for the packing once.
+enum AggMode { kPlain = 0, kParts = 1, kPacked = 2 };
+
+// Column index (and, kPacked, the scale `ms`) of edge `base + gl` (0 / 0.f past the end of the row).
+template <int MODE>
+__device__ __forceinline__ void load_col(const AggParams& p, int base, int end, int gl, int& c, float& ms) {
   c = 0;
+  ms = 0.f;
   const int e = base + gl;
-  if (e < end) c = ld_stream(p.col + e);
+  if (e < end) {
+    if constexpr (MODE == kPacked) {
+      const int2 m = __ldcs(p.meta + e);
+      c = m.x;
+      ms = __int_as_float(m.y);
+    } else {
+      c = ld_stream(p.col + e);
+    }
+  }
 }
-__device__ __forceinline__ void load_scale(const AggParams& p, int base, int end, int gl, int c, float& s) {
+// Combined scale of edge `base + gl` whose column `c` has arrived (0.f past the end of the row).
+template <int MODE>
+__device__ __forceinline__ void load_scale(const AggParams& p, int base, int end, int gl, int c, float ms, float& s) {
+  if constexpr (MODE == kPacked) {
+    s = ms;
+    return;
+  }
   s = 0.f;
   const int e = base + gl;
   if (e < end) {
@@ -112,32 +142,37 @@ __device__ __forceinline__ void load_scale(const AggParams& p, int base, int end
 // starting at batch `first`.  All lanes of a group execute this together.
 // (my_c, my_s) = column / scale of the first batch, loaded by the caller (so that a caller can
 // have them in flight long before the row is processed).
-// Neighbour-row loads of one lane: lane column offsets are clamped into the row (lanes past `width`
-// re-read column 0 and their sums are never written), so the steady state carries no per-load
-// predicate, and a row address is ONE IMAD.WIDE off a per-lane base pointer.  PARTS = source matrix
-// row-partitioned over peer GPUs (cold path, stg_agg_scaled_sum_parts_f32).
-template <int VEC, int GROUP, int NACC, bool PARTS>
+// Neighbour-row loads of one lane: a row address is ONE IMAD.WIDE off a per-lane base pointer; lanes past
+// `width` are switched off by a loop-invariant predicate (their sums are never written).
+template <int VEC, int GROUP, int NACC, int MODE>
 struct RowLoader {
   using T = typename VecT<VEC>::type;
   const char* base[NACC];
   int off[NACC];
+  bool live[NACC];        // lane-constant: this lane's chunk k lies inside the row
   unsigned ld_bytes;
   __device__ __forceinline__ RowLoader(const AggParams& p, int gl) {
     ld_bytes = static_cast<unsigned>(p.ld) * 4u;
 #pragma unroll
     for (int k = 0; k < NACC; ++k) {
       int o = (gl + k * GROUP) * VEC;
-      if (o >= p.width) o = 0;
+      live[k] = o < p.width;
+      if (!live[k]) o = (p.width - 1) / VEC * VEC;
       off[k] = o;
       base[k] = reinterpret_cast<const char*>(p.x + o);
     }
   }
+  // Idle lanes (F=100: lanes 25..31) are predicated off with a loop-invariant predicate: a lane that does not
+  // load costs no LSU write-back slot, and the write-back of 32 x 16 bytes per row is what bounds F = 68..124.
   __device__ __forceinline__ T load(const AggParams& p, int c, int k) const {
-    if constexpr (PARTS) {
-      return ld_row<VEC>(src_row(p, c) + off[k]);
+    T v;
+    zero_vec(v);
+    if constexpr (MODE == kParts) {
+      v = ld_row<VEC>(src_row(p, c) + off[k]);
     } else {
-      return __ldg(reinterpret_cast<const T*>(base[k] + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
+      if (live[k]) v = __ldg(reinterpret_cast<const T*>(base[k] + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
     }
+    return v;
   }
 };
 
@@ -145,13 +180,13 @@ struct RowLoader {
 // starting at batch `first`.  All lanes of a group execute this together.
 // (my_c, my_s) = column / scale of the first batch, loaded by the caller (so that a caller can
 // have them in flight long before the row is processed).
-template <int VEC, int GROUP, int NACC, int UNROLL_ = 0, bool PARTS = false>
+template <int VEC, int GROUP, int NACC, int UNROLL_ = 0, int MODE = kPlain>
 __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
                                                  int batch_step, int gl, unsigned gmask,
                                                  typename VecT<VEC>::type (&acc)[NACC], int my_c, float my_s) {
   using T = typename VecT<VEC>::type;
   constexpr int UNROLL = UNROLL_ > 0 ? (UNROLL_ < GROUP ? UNROLL_ : GROUP) : (GROUP >= 8 ? 8 : GROUP) / (NACC > 2 ? 2 : 1);
-  const RowLoader<VEC, GROUP, NACC, PARTS> rows(p, gl);
+  const RowLoader<VEC, GROUP, NACC, MODE> rows(p, gl);
 
   // (column, scale) of the batch a lane group is summing reach the other lanes either by two SHFL per edge
   // or through shared memory (one STS.64 per lane + one LDS.128 per TWO edges).  A/B on one box, config 5:
@@ -184,15 +219,15 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
 
   int base = beg + first_batch * GROUP;
   int nx_c;
-  float nx_s;
+  float nx_m, nx_s;
   for (; base < end; base += batch_step * GROUP) {
     if constexpr (kSmemMeta) {
       __syncwarp(gmask);                                     // the previous batch has been read by every lane
       meta[threadIdx.x] = make_int2(my_c, __float_as_int(my_s));
       __syncwarp(gmask);
     }
-    load_col(p, base + batch_step * GROUP, end, gl, nx_c);   // prefetch next batch
-    load_scale(p, base + batch_step * GROUP, end, gl, nx_c, nx_s);
+    load_col<MODE>(p, base + batch_step * GROUP, end, gl, nx_c, nx_m);   // prefetch next batch
+    load_scale<MODE>(p, base + batch_step * GROUP, end, gl, nx_c, nx_m, nx_s);
     const int n = min(GROUP, end - base);
     int j = 0;
     for (; j + UNROLL <= n; j += UNROLL) {     // full groups: UNROLL unpredicated row loads in flight
@@ -235,15 +270,126 @@ __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, in
   }
 }
 
-template <int VEC, int GROUP, int NACC, bool PARTS = false>
+template <int VEC, int GROUP, int NACC, int MODE = kPlain>
 __device__ __forceinline__ void accumulate_edges(const AggParams& p, int beg, int end, int first_batch,
                                                  int batch_step, int gl, unsigned gmask,
                                                  typename VecT<VEC>::type (&acc)[NACC]) {
   int c;
-  float s;
-  load_col(p, beg + first_batch * GROUP, end, gl, c);
-  load_scale(p, beg + first_batch * GROUP, end, gl, c, s);
-  accumulate_edges<VEC, GROUP, NACC, 0, PARTS>(p, beg, end, first_batch, batch_step, gl, gmask, acc, c, s);
+  float m, s;
+  load_col<MODE>(p, beg + first_batch * GROUP, end, gl, c, m);
+  load_scale<MODE>(p, beg + first_batch * GROUP, end, gl, c, m, s);
+  accumulate_edges<VEC, GROUP, NACC, 0, MODE>(p, beg, end, first_batch, batch_step, gl, gmask, acc, c, s);
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor_vec(T v, int o);
+template <>
+__device__ __forceinline__ float shfl_xor_vec<float>(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <>
+__device__ __forceinline__ float2 shfl_xor_vec<float2>(float2 v, int o) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+template <>
+__device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
+                     __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
+}
+
+
+// PAIR form of the edge loop for one row per warp with 16 < F/4 <= 32 (F = 68..128): the two half-warps
+// sum ALTERNATE edges of the row, each half covering the row with 16 lanes x 2 float4 chunks, so ONE
+// SHFL.IDX pair (per-lane source: lane j + half) hands two edges their {column, scale}.  ncu on config 5,
+// F=100 (profiles/r01_agg_ncu.md): the LSU data pipe is the busiest unit (77 % of peak), and the two
+// 32-lane broadcasts per edge are a third of its wavefronts; the halves' partial sums are merged once per
+// row with four SHFL.BFLY.  Fixed order: deterministic.  On return lane L holds the row's floats [4L, 4L+4).
+template <int UNROLL, int MODE>
+__device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int beg, int end, int lane, float4& result,
+                                                      int my_c, float my_m, float my_s) {
+  static_assert(UNROLL % 2 == 0, "two edges per step");
+  constexpr int STEPS = UNROLL / 2;
+  const int half = lane >> 4;
+  const int hl = lane & 15;
+  const unsigned ld_bytes = static_cast<unsigned>(p.ld) * 4u;
+  const char* base0;
+  const char* base1;
+  {
+    const int last = (p.width - 1) / 4 * 4;
+    int o0 = hl * 4, o1 = (hl + 16) * 4;
+    if (o0 > last) o0 = last;
+    if (o1 > last) o1 = last;
+    base0 = reinterpret_cast<const char*>(p.x + o0);
+    base1 = reinterpret_cast<const char*>(p.x + o1);
+  }
+  const bool live1 = (hl + 16) * 4 < p.width;   // chunk 0 is always inside the row (width > 64); F=100: 9 of 16 lanes
+  auto row0 = [&](int c) { return __ldg(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
+  auto row1 = [&](int c) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live1) v = __ldg(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
+    return v;
+  };
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  (void)my_m;
+  for (int base = beg; base < end; base += 32) {
+    int nx_c;
+    float nx_m, nx_s;
+    load_col<MODE>(p, base + 32, end, lane, nx_c, nx_m);   // prefetch next batch
+    load_scale<MODE>(p, base + 32, end, lane, nx_c, nx_m, nx_s);
+    const int n = min(32, end - base);
+    int j = 0;
+    for (; j + UNROLL <= n; j += UNROLL) {     // full groups: UNROLL edges = STEPS unpredicated steps per half
+      int c[STEPS];
+      float sc[STEPS];
+      float4 v0[STEPS], v1[STEPS];
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        c[u] = __shfl_sync(0xffffffffu, my_c, j + 2 * u + half);
+        sc[u] = __shfl_sync(0xffffffffu, my_s, j + 2 * u + half);
+      }
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        v0[u] = row0(c[u]);
+        v1[u] = row1(c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        fma_vec(acc0, sc[u], v0[u]);
+        fma_vec(acc1, sc[u], v1[u]);
+      }
+    }
+    if (j < n) {                               // last, partial group of the batch
+      int c[STEPS];
+      float sc[STEPS];
+      float4 v0[STEPS], v1[STEPS];
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        c[u] = __shfl_sync(0xffffffffu, my_c, (j + 2 * u + half) & 31);
+        sc[u] = __shfl_sync(0xffffffffu, my_s, (j + 2 * u + half) & 31);
+      }
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        if ((j + 2 * u + half) < n) {
+          v0[u] = row0(c[u]);
+          v1[u] = row1(c[u]);
+        } else {
+          zero_vec(v0[u]);
+          zero_vec(v1[u]);
+          sc[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < STEPS; ++u) {
+        fma_vec(acc0, sc[u], v0[u]);
+        fma_vec(acc1, sc[u], v1[u]);
+      }
+    }
+    my_c = nx_c;
+    my_s = nx_s;
+  }
+  // merge the halves: lane L (half 0) owns chunk 0 = floats [4L, 4L+4), lane L (half 1) owns chunk 1 = [4L, 4L+4) too
+  const float4 give = half ? acc0 : acc1;      // what the partner lane owns
+  float4 mine = half ? acc1 : acc0;
+  add_vec(mine, shfl_xor_vec<float4>(give, 16));
+  result = mine;
 }
 
 // Scaled row result -> out (assign / += / red.add).
@@ -251,7 +397,7 @@ template <int VEC, int GROUP, int NACC>
 __device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, bool nonempty, float r,
                                           typename VecT<VEC>::type (&acc)[NACC]) {
   using T = typename VecT<VEC>::type;
-  float* dst = p.out + static_cast<size_t>(row) * p.ld;
+  float* dst = p.out + static_cast<size_t>(row) * p.ld_out;
 #pragma unroll
   for (int k = 0; k < NACC; ++k) {
     const int o = (gl + k * GROUP) * VEC;
@@ -274,7 +420,7 @@ __device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, b
 // (row_offset -> column index -> neighbour scale -> neighbour rows) is spread over four consecutive
 // loop iterations: while row i is being summed, the scales of row i+1, the columns of row i+2 and
 // the offsets of row i+3 are already in flight.
-template <int VEC, int GROUP, int NACC, int MINB, int UNROLL>
+template <int VEC, int GROUP, int NACC, int MINB, int UNROLL, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(const AggParams p, int slots_per_block) {
   using T = typename VecT<VEC>::type;
   constexpr int GPW = 32 / GROUP;
@@ -309,7 +455,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   int slot0, row0, beg0, end0, c0;     // row being summed (scale loaded at the top of the iteration)
   int row1, beg1, end1, c1;            // columns in flight
   int row2, beg2, end2;                // offsets in flight
-  float s0, r0;
+  float s0, r0, m0, m1;                // m*: scale that arrived WITH the column (kPacked)
   slot0 = draw();
   if (slot0 >= last) return;
   stage_a(slot0, row0, beg0, end0);
@@ -318,10 +464,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   int slot2 = draw();
   stage_a(slot2, row2, beg2, end2);
   drop_hub(beg0, end0);
-  load_col(p, beg0, end0, gl, c0);
+  load_col<MODE>(p, beg0, end0, gl, c0, m0);
   drop_hub(beg1, end1);
-  load_col(p, beg1, end1, gl, c1);
-  load_scale(p, beg0, end0, gl, c0, s0);
+  load_col<MODE>(p, beg1, end1, gl, c1, m1);
+  load_scale<MODE>(p, beg0, end0, gl, c0, m0, s0);
   r0 = (end0 >= 0 && p.rs) ? __ldg(p.rs + row0) : 1.f;
 
   while (slot0 < last) {
@@ -331,26 +477,32 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
     stage_a(slot3, row3, beg3, end3);
     drop_hub(beg2, end2);
     int c2;
-    load_col(p, beg2, end2, gl, c2);
+    float m2;
+    load_col<MODE>(p, beg2, end2, gl, c2, m2);
     float s1;
-    load_scale(p, beg1, end1, gl, c1, s1);
+    load_scale<MODE>(p, beg1, end1, gl, c1, m1, s1);
     const float r1 = (end1 >= 0 && p.rs) ? __ldg(p.rs + row1) : 1.f;
 
     if (end0 >= 0) {
       T acc[NACC];
+      if constexpr (PAIR) {
+        static_assert(VEC == 4 && GROUP == 32 && NACC == 1, "pair form: one row per warp, float4 lanes");
+        accumulate_edges_pair<UNROLL, MODE>(p, beg0, end0, lane, acc[0], c0, 0.f, s0);
+      } else {
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-      accumulate_edges<VEC, GROUP, NACC, UNROLL>(p, beg0, end0, 0, 1, gl, gmask, acc, c0, s0);
+        for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+        accumulate_edges<VEC, GROUP, NACC, UNROLL, MODE>(p, beg0, end0, 0, 1, gl, gmask, acc, c0, s0);
+      }
       write_row<VEC, GROUP, NACC>(p, row0, gl, end0 > beg0, r0, acc);
     }
     slot0 = slot1; row0 = row1; beg0 = beg1; end0 = end1; c0 = c1; s0 = s1; r0 = r1;
-    slot1 = slot2; row1 = row2; beg1 = beg2; end1 = end2; c1 = c2;
+    slot1 = slot2; row1 = row2; beg1 = beg2; end1 = end2; c1 = c2; m1 = m2;
     slot2 = slot3; row2 = row3; beg2 = beg3; end2 = end3;
   }
   grid_dependency_wait();
 }
 
-template <int VEC, int GROUP, int NACC, bool PARTS>
+template <int VEC, int GROUP, int NACC, int MODE>
 __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
@@ -367,7 +519,7 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   T acc[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-  accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, 0, 1, gl, gmask, acc);
+  accumulate_edges<VEC, GROUP, NACC, MODE>(p, beg, end, 0, 1, gl, gmask, acc);
 
   const int orow = p.out_rows ? __ldg(p.out_rows + row) : row;
   const float r = p.rs ? __ldg(p.rs + orow) : 1.f;
@@ -389,21 +541,7 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
 constexpr int kHubCluster = 8;
 constexpr int kClusterRowEdges = 8192;
 
-template <typename T>
-__device__ __forceinline__ T shfl_xor_vec(T v, int o);
-template <>
-__device__ __forceinline__ float shfl_xor_vec<float>(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-template <>
-__device__ __forceinline__ float2 shfl_xor_vec<float2>(float2 v, int o) {
-  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
-}
-template <>
-__device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
-  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
-                     __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
-}
-
-template <int VEC, int GROUP, int NACC, bool PARTS>
+template <int VEC, int GROUP, int NACC, int MODE>
 __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThreads)
     agg_hub_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
@@ -433,7 +571,7 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
     T acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-    accumulate_edges<VEC, GROUP, NACC, PARTS>(p, beg, end, slot, slots, gl, gmask, acc);
+    accumulate_edges<VEC, GROUP, NACC, MODE>(p, beg, end, slot, slots, gl, gmask, acc);
 #pragma unroll
     for (int o = GROUP; o < 32; o <<= 1) {        // groups of one warp -> lanes [0, GROUP)
 #pragma unroll
@@ -528,7 +666,16 @@ cudaError_t launch_overlapped(void (*kernel)(KArgs...), int blocks, int threads,
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-template <int VEC, int GROUP, int NACC, bool PARTS>
+// A/B switch while the pair form is being measured (STG_AGG_PAIR=0/1; read once).
+inline bool pair_mode() {
+  static const bool on = [] {
+    const char* e = getenv("STG_AGG_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+template <int VEC, int GROUP, int NACC, int MODE>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
   const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
@@ -539,42 +686,66 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
   const bool overlap = hubs && p.num_edges >= (1 << 20);
   if (hubs) {
-    agg_hub_kernel<VEC, GROUP, NACC, PARTS><<<2 * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC, MODE><<<2 * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
-    if constexpr (GROUP == 32 && !PARTS) {
+    if constexpr (GROUP == 32 && MODE != kParts) {
       // measured on config 5 (F=100 / 128): 3.48 / 3.34 ms against 3.99 / 3.88 ms for one row per warp;
       // 4 resident blocks per SM beat 3 (4.2 ms) and 2 (5.2 ms), 5..8 with a shorter unroll do not help.
       constexpr int kRowsPerWarp = 32;
       constexpr int MINB = 4;           // 8 / NACC neighbour rows in flight per lane keep this at <= 64 registers
       constexpr int slots_per_block = (kBlockThreads / 32) * kRowsPerWarp;
       const int pblocks = (p.num_rows + slots_per_block - 1) / slots_per_block;
-      STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC>, pblocks, kBlockThreads, stream,
+      if constexpr (VEC == 4 && NACC == 1) {
+        if (p.width > 64 && pair_mode()) {
+          STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true>, pblocks, kBlockThreads,
+                                     stream, overlap, p, slots_per_block));
+          STG_LAUNCH_CHECK("agg_rows_pipe_kernel (pair)");
+          return STG_OK;
+        }
+      }
+      STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC, MODE>, pblocks, kBlockThreads, stream,
                                  overlap, p, slots_per_block));
     } else {
       // narrow rows (several rows per warp): the lane groups of a warp diverge and the queue costs
       // more than it saves (F=64: 3.0 ms against 2.66 ms)
-      STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC, PARTS>, blocks, kBlockThreads, stream, overlap, p));
+      STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC, MODE>, blocks, kBlockThreads, stream, overlap, p));
     }
     STG_LAUNCH_CHECK("agg_rows_kernel");
   }
   return STG_OK;
 }
 
-template <int VEC, bool PARTS>
+template <int VEC, int MODE>
 int dispatch_group(const AggParams& p, cudaStream_t stream, int avg_degree) {
   const int nvec = p.width / VEC;
   // (A 8-lane x 4-chunk geometry for short rows was measured for the halo-source pass: slower, 0.40 vs 0.28 ms.)
   (void)avg_degree;
-  if (nvec <= 1) return launch_agg<VEC, 1, 1, PARTS>(p, stream);
-  if (nvec <= 2) return launch_agg<VEC, 2, 1, PARTS>(p, stream);
-  if (nvec <= 4) return launch_agg<VEC, 4, 1, PARTS>(p, stream);
-  if (nvec <= 8) return launch_agg<VEC, 8, 1, PARTS>(p, stream);
-  if (nvec <= 16) return launch_agg<VEC, 16, 1, PARTS>(p, stream);
-  if (nvec <= 32) return launch_agg<VEC, 32, 1, PARTS>(p, stream);
-  if (nvec <= 64) return launch_agg<VEC, 32, 2, PARTS>(p, stream);
-  return launch_agg<VEC, 32, 4, PARTS>(p, stream);
+  if (nvec <= 1) return launch_agg<VEC, 1, 1, MODE>(p, stream);
+  if (nvec <= 2) return launch_agg<VEC, 2, 1, MODE>(p, stream);
+  if (nvec <= 4) return launch_agg<VEC, 4, 1, MODE>(p, stream);
+  if (nvec <= 8) return launch_agg<VEC, 8, 1, MODE>(p, stream);
+  if (nvec <= 16) return launch_agg<VEC, 16, 1, MODE>(p, stream);
+  if (nvec <= 32) return launch_agg<VEC, 32, 1, MODE>(p, stream);
+  if (nvec <= 64) return launch_agg<VEC, 32, 2, MODE>(p, stream);
+  return launch_agg<VEC, 32, 4, MODE>(p, stream);
+}
+
+// {column, nbr_scale[column] * edge_scale[eid]} of every CSR slot, in CSR order (same product order as
+// load_scale<kPlain>, so the packed and the plain path give bit-identical sums).
+__global__ void __launch_bounds__(256) pack_edge_meta_kernel(const AggParams p, int2* __restrict__ meta) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.num_edges; e += stride) {
+    const int c = ld_stream(p.col + e);
+    float sc = 1.f;
+    if (p.ns) sc = __ldg(p.ns + c);
+    if (p.es) {
+      const int eid = p.eids_identity ? e : (ld_stream(p.eids + e) - p.eid_base);
+      sc *= __ldg(p.es + eid);
+    }
+    __stcs(meta + e, make_int2(c, __float_as_int(sc)));
+  }
 }
 
 }  // namespace
@@ -582,9 +753,11 @@ int dispatch_group(const AggParams& p, cudaStream_t stream, int avg_degree) {
 int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, const float* ns,
                           const float* es, const float* rs, float* out, cudaStream_t stream,
                           int nparts = 0, const float* const* parts = nullptr, const int32_t* bounds = nullptr,
-                          int accumulate = 0, const int32_t* out_rows = nullptr) {
+                          int accumulate = 0, const int32_t* out_rows = nullptr, const StgEdgeMeta* meta = nullptr,
+                          int x_ld = 0, int out_ld = 0) {
   AggParams p;
   p.out_rows = out_rows;
+  p.meta = reinterpret_cast<const int2*>(meta);
   p.accumulate = accumulate;
   p.nparts = nparts;
   for (int q = 0; q < STG_MAX_PARTS; ++q) p.xs[q] = q < nparts ? parts[q] : nullptr;
@@ -600,7 +773,8 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   p.eids_identity = g->eids_identity;
   p.hub_threshold = (g->hub_rows && g->hub_count) ? g->hub_threshold : 0;
   p.hub_capacity = g->hub_capacity;
-  p.ld = feat;
+  p.ld = x_ld > 0 ? x_ld : feat;
+  p.ld_out = out_ld > 0 ? out_ld : feat;
   p.ns = ns;
   p.es = es;
   p.rs = rs;
@@ -614,8 +788,8 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
     al8 = al8 && aligned8(parts[q]);
   }
   int vec = 1;
-  if (feat % 4 == 0 && al16) vec = 4;
-  else if (feat % 2 == 0 && al8) vec = 2;
+  if (feat % 4 == 0 && p.ld % 4 == 0 && p.ld_out % 4 == 0 && al16) vec = 4;
+  else if (feat % 2 == 0 && p.ld % 2 == 0 && p.ld_out % 2 == 0 && al8) vec = 2;
   const int chunk = 32 * 4 * vec;  // widest tile one launch covers
   for (int f0 = 0; f0 < feat; f0 += chunk) {
     p.x = x ? x + f0 : nullptr;
@@ -625,13 +799,17 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
     int rc;
     const int avg_degree = g->num_nodes > 0 ? g->num_edges / g->num_nodes : -1;
     if (nparts > 0) {
-      if (vec == 4) rc = dispatch_group<4, true>(p, stream, avg_degree);
-      else if (vec == 2) rc = dispatch_group<2, true>(p, stream, avg_degree);
-      else rc = dispatch_group<1, true>(p, stream, avg_degree);
+      if (vec == 4) rc = dispatch_group<4, kParts>(p, stream, avg_degree);
+      else if (vec == 2) rc = dispatch_group<2, kParts>(p, stream, avg_degree);
+      else rc = dispatch_group<1, kParts>(p, stream, avg_degree);
+    } else if (meta != nullptr) {
+      if (vec == 4) rc = dispatch_group<4, kPacked>(p, stream, avg_degree);
+      else if (vec == 2) rc = dispatch_group<2, kPacked>(p, stream, avg_degree);
+      else rc = dispatch_group<1, kPacked>(p, stream, avg_degree);
     } else {
-      if (vec == 4) rc = dispatch_group<4, false>(p, stream, avg_degree);
-      else if (vec == 2) rc = dispatch_group<2, false>(p, stream, avg_degree);
-      else rc = dispatch_group<1, false>(p, stream, avg_degree);
+      if (vec == 4) rc = dispatch_group<4, kPlain>(p, stream, avg_degree);
+      else if (vec == 2) rc = dispatch_group<2, kPlain>(p, stream, avg_degree);
+      else rc = dispatch_group<1, kPlain>(p, stream, avg_degree);
     }
     if (rc != STG_OK) return rc;
   }
@@ -753,4 +931,47 @@ STG_API int stg_agg_scaled_sum_red_f32(const StgCsrView* g, const float* x, int3
   STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
   STG_CHECK_ARG(x != out, "x and out must not alias");
   return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream), 0, nullptr, nullptr, 2);
+}
+
+STG_API int stg_csr_pack_edge_meta_f32(const StgCsrView* g, const float* nbr_scale, const float* edge_scale,
+                                       StgEdgeMeta* meta, void* stream) {
+  int rc = validate_view(g, edge_scale != nullptr);
+  if (rc != STG_OK) return rc;
+  if (g->num_edges == 0) return STG_OK;
+  STG_CHECK_ARG(meta != nullptr && aligned8(meta), "meta must be a non-NULL, 8-byte aligned device pointer");
+  AggParams p = {};
+  p.col = g->column_indices;
+  p.eids = g->eids;
+  p.num_edges = g->num_edges;
+  p.eid_base = g->eid_base;
+  p.eids_identity = g->eids_identity;
+  p.ns = nbr_scale;
+  p.es = edge_scale;
+  const int blocks = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(g->num_edges) + 255) / 256, 8 * sm_count()));
+  pack_edge_meta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<int2*>(meta));
+  STG_LAUNCH_CHECK("pack_edge_meta_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_agg_packed_sum_strided_f32(const StgCsrView* g, const StgEdgeMeta* meta, const float* x, int32_t feat,
+                                           int32_t x_ld, const float* row_scale, float* out, int32_t out_ld,
+                                           int32_t accumulate, void* stream) {
+  int rc = validate_view(g, false);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  STG_CHECK_ARG(x_ld >= feat && out_ld >= feat, "row strides (%d, %d) must be >= feat (%d)", x_ld, out_ld, feat);
+  STG_CHECK_ARG(accumulate >= 0 && accumulate <= 2, "accumulate must be 0, 1 or 2 (got %d)", accumulate);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(g->num_edges == 0 || (meta != nullptr && aligned8(meta)),
+                "meta must be a non-NULL, 8-byte aligned device pointer");
+  STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
+  STG_CHECK_ARG(x != out, "x and out must not alias");
+  // an empty graph has nothing to read through meta: the plain path writes the zero rows
+  return agg_scaled_sum_device(g, x, feat, nullptr, nullptr, row_scale, out, as_stream(stream), 0, nullptr, nullptr,
+                               accumulate, nullptr, g->num_edges == 0 ? nullptr : meta, x_ld, out_ld);
+}
+
+STG_API int stg_agg_packed_sum_f32(const StgCsrView* g, const StgEdgeMeta* meta, const float* x, int32_t feat,
+                                   const float* row_scale, float* out, int32_t accumulate, void* stream) {
+  return stg_agg_packed_sum_strided_f32(g, meta, x, feat, feat, row_scale, out, feat, accumulate, stream);
 }

@@ -19,6 +19,10 @@ from ... import _lib
 
 #: rows longer than this are processed by the block-per-row kernel (agg.cu)
 HUB_THRESHOLD = int(os.environ.get("STG_HUB_THRESHOLD", "1024"))
+#: STG_PACK_META=0 keeps static graphs on the plain (unpacked) aggregation kernel (A/B runs)
+PACK_META = os.environ.get("STG_PACK_META", "1") != "0"
+#: a CSR that had to repack more often than this (its scales are per-call temporaries) falls back to the plain kernel
+MAX_META_REPACKS = 16
 
 
 def _edges_to_device(edge_list, device):
@@ -65,6 +69,10 @@ class CSR:
         self._hub_count = None
         self._hub_enabled = None
         self._view = None
+        #: static graphs cache the packed {col, scale} array per scale tensor (see packed_meta)
+        self.pack_enabled = False
+        self._meta_cache = []
+        self._meta_misses = 0
 
     # -- reference-compatible surface ---------------------------------------
     @property
@@ -96,6 +104,34 @@ class CSR:
         if self.weighted_row_degrees is None:
             return [0.0] * self.num_nodes
         return self.weighted_row_degrees.cpu().tolist()
+
+    # -- packed edge metadata (stg_csr_pack_edge_meta_f32) -------------------------
+    def packed_meta(self, nbr_scale, edge_scale):
+        """``{col, nbr_scale[col] * edge_scale[eid]}`` per CSR slot for these scale tensors, packed on first use.
+
+        The cache key is (address, in-place version counter) of each scale tensor, and the entry keeps the
+        tensors alive, so an address cannot be recycled under it; an in-place update through torch bumps the
+        version and repacks.  Returns None (-> plain kernel) when there is nothing to pack, when packing is
+        disabled, or on a miss during CUDA-graph capture (the cache must not own capture-pool memory).
+        """
+        if not PACK_META or (nbr_scale is None and edge_scale is None) or self.num_edges == 0:
+            return None
+        key = tuple((t.data_ptr(), t._version, t.numel()) if t is not None else None for t in (nbr_scale, edge_scale))
+        for k, _, meta in self._meta_cache:
+            if k == key:
+                return meta
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        self._meta_misses += 1
+        if self._meta_misses > MAX_META_REPACKS:   # scales that change every call (an intermediate tensor): stop packing
+            self.pack_enabled = False
+            self._meta_cache = []
+            return None
+        from ... import kernels
+
+        meta = kernels.pack_edge_meta(self.view(), nbr_scale, edge_scale, device=self.row_offset.device)
+        self._meta_cache = [(key, (nbr_scale, edge_scale), meta)] + self._meta_cache[:1]   # at most two live entries
+        return meta
 
     # -- C-ABI view ------------------------------------------------------------
     def prepare_hub_schedule(self, sync: bool = True):

@@ -37,6 +37,7 @@ class StaticGraph(STGraphBase):
         self._num_edges = int(n_unique.item())
         self._forward_graph.prepare_hub_schedule(sync=True)
         self._backward_graph.prepare_hub_schedule(sync=True)
+        self._forward_graph.pack_enabled = self._backward_graph.pack_enabled = True
 
         self.edge_weights = None
         if edge_weights is not None and len(edge_weights) > 0:

@@ -80,6 +80,101 @@ def agg_scaled_sum(view: _lib.StgCsrView, x: torch.Tensor, nbr_scale=None, edge_
     return out
 
 
+def pack_edge_meta(view: _lib.StgCsrView, nbr_scale=None, edge_scale=None, out: torch.Tensor | None = None,
+                   device=None) -> torch.Tensor:
+    """``meta[e] = {col[e], nbr_scale[col[e]] * edge_scale[eid(e)]}`` per CSR slot as an int32 ``[E, 2]`` tensor
+    (``stg_csr_pack_edge_meta_f32``); feed it to :func:`agg_packed_sum`."""
+    global launch_count
+    for nm, t in (("nbr_scale", nbr_scale), ("edge_scale", edge_scale)):
+        if t is not None:
+            _check(t, nm)
+    if edge_scale is not None and edge_scale.numel() < view.num_edges:
+        raise ValueError(f"edge_scale has {edge_scale.numel()} elements for {view.num_edges} edges")
+    if out is None:
+        ref = nbr_scale if nbr_scale is not None else edge_scale
+        dev = device if device is not None else (ref.device if ref is not None else torch.device("cuda", torch.cuda.current_device()))
+        out = torch.empty(view.num_edges, 2, dtype=torch.int32, device=dev)
+    else:
+        _check(out, "out", torch.int32)
+        if out.numel() != 2 * view.num_edges:
+            raise ValueError(f"meta must be int32 [{view.num_edges}, 2]")
+    if view.num_edges == 0:
+        return out
+    _lib.call("stg_csr_pack_edge_meta_f32", ctypes.byref(view), _lib.ptr(nbr_scale), _lib.ptr(edge_scale), out.data_ptr(),
+              _lib.current_stream_ptr())
+    launch_count += 1
+    return out
+
+
+def padded_rows(rows: int, feat: int, device, dtype=torch.float32) -> torch.Tensor:
+    """``[rows, feat]`` view whose rows start on 128-byte lines (row stride = feat rounded up to 32 floats).
+
+    :func:`agg_packed_sum` takes such views (and any other 2-D view with dense rows) as ``x`` / ``out``.  Measured on
+    config 5 (F=100): no faster than the dense layout -- kept for in-place aggregation of column blocks.
+    """
+    ld = (feat + 31) // 32 * 32
+    return torch.empty(rows, ld, dtype=dtype, device=device)[:, :feat]
+
+
+def _row_stride(t: torch.Tensor, name: str) -> int:
+    """Row stride (floats) of a 2-D fp32 CUDA tensor whose rows are dense (``stride(1) == 1``)."""
+    if t.dim() == 2 and not t.is_contiguous():
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must live on a CUDA device (stgraph_b200 has no CPU path)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be torch.float32, got {t.dtype}")
+        if t.shape[1] > 0 and (t.stride(1) != 1 or t.stride(0) < t.shape[1]):
+            raise ValueError(f"{name} must have dense rows (stride(1) == 1, stride(0) >= feat)")
+        return int(t.stride(0))
+    _check(t, name)
+    return t.numel() // max(t.shape[0], 1)
+
+
+def agg_packed_sum(view: _lib.StgCsrView, meta: torch.Tensor, x: torch.Tensor, row_scale=None,
+                   out: torch.Tensor | None = None, accumulate=False, stream=None) -> torch.Tensor:
+    """``out[r] = row_scale[r] * sum_e meta[e].scale * x[meta[e].col]`` (``stg_agg_packed_sum_strided_f32``): the sums
+    of :func:`agg_scaled_sum`, bit for bit, with one coalesced 8-byte load per edge instead of dependent gathers.
+    ``x`` / ``out`` may be row-padded 2-D views (:func:`padded_rows`)."""
+    global launch_count
+    x_ld = _row_stride(x, "x")
+    _check(meta, "meta", torch.int32)
+    n = view.num_nodes
+    if meta.numel() < 2 * view.num_edges:
+        raise ValueError(f"meta has {meta.numel() // 2} entries for {view.num_edges} edges")
+    if x.dim() < 2:
+        raise ValueError("x must be [rows, feat...]")
+    feat = x.shape[1] if x.dim() == 2 else x.numel() // max(x.shape[0], 1)
+    if row_scale is not None:
+        _check(row_scale, "row_scale")
+        if row_scale.numel() != n:
+            raise ValueError(f"row_scale must have {n} elements, got {row_scale.numel()}")
+    if out is None:
+        if x.shape[0] != n:
+            raise ValueError(f"x has {x.shape[0]} rows for a view of {n} rows: pass out= for a row slice")
+        out = padded_rows(n, feat, x.device) if x_ld != feat else torch.empty_like(x)
+    out_ld = _row_stride(out, "out")
+    if out.shape[0] != n or out.numel() != n * feat:
+        raise ValueError(f"out must be [{n}, {feat}], got {tuple(out.shape)}")
+    if n == 0 or feat == 0:
+        return out
+    _lib.call("stg_agg_packed_sum_strided_f32", ctypes.byref(view), meta.data_ptr(), x.data_ptr(), feat, x_ld,
+              _lib.ptr(row_scale), out.data_ptr(), out_ld, {False: 0, True: 1, "red": 2}[accumulate],
+              stream if stream is not None else _lib.current_stream_ptr())
+    launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
+    return out
+
+
+def agg_scaled_sum_graph(csr, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
+                         out: torch.Tensor | None = None) -> torch.Tensor:
+    """:func:`agg_scaled_sum` over one direction of a graph object (``graph/static/csr.py:CSR``).  A static CSR
+    keeps the packed ``{col, scale}`` array of the scales it was last called with (``CSR.packed_meta``), so every
+    call after the first runs the packed kernel; dynamic snapshots and unscaled sums take the plain kernel."""
+    meta = csr.packed_meta(nbr_scale, edge_scale) if getattr(csr, "pack_enabled", False) else None
+    if meta is None:
+        return agg_scaled_sum(csr.view(), x, nbr_scale, edge_scale, row_scale, out=out)
+    return agg_packed_sum(csr.view(), meta, x, row_scale, out=out)
+
+
 def agg_scaled_sum_host(view: _lib.StgCsrView, x_host: torch.Tensor, out_host: torch.Tensor, scratch: torch.Tensor,
                         nbr_scale_host=None, edge_scale_host=None, row_scale_host=None):
     """Host-buffer variant (H2D + kernel + D2H inside one C call); buffers should be pinned."""

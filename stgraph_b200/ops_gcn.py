@@ -21,7 +21,10 @@ class _GcnAggregate(torch.autograd.Function):
         h = h.contiguous()
         nflat = norm.reshape(-1)
         wflat = edge_weight.reshape(-1) if edge_weight is not None else None
-        out = kernels.agg_scaled_sum(fwd_view, h, nflat, wflat, nflat)
+        if getattr(keepalive[0], "pack_enabled", False):   # static graph: packed {col, scale} array, built on first use
+            out = kernels.agg_scaled_sum_graph(keepalive[0], h, nflat, wflat, nflat)
+        else:
+            out = kernels.agg_scaled_sum(fwd_view, h, nflat, wflat, nflat)
         ctx.bwd_view, ctx.keepalive = bwd_view, keepalive
         ctx.save_for_backward(nflat, wflat if wflat is not None else nflat)
         ctx.weighted = wflat is not None
@@ -30,7 +33,11 @@ class _GcnAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         nflat, wflat = ctx.saved_tensors
-        gh = kernels.agg_scaled_sum(ctx.bwd_view, gout.contiguous(), nflat, wflat if ctx.weighted else None, nflat)
+        wb = wflat if ctx.weighted else None
+        if getattr(ctx.keepalive[1], "pack_enabled", False):
+            gh = kernels.agg_scaled_sum_graph(ctx.keepalive[1], gout.contiguous(), nflat, wb, nflat)
+        else:
+            gh = kernels.agg_scaled_sum(ctx.bwd_view, gout.contiguous(), nflat, wb, nflat)
         return None, None, None, gh, None, None
 
 
