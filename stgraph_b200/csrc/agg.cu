@@ -88,11 +88,6 @@ __device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
   return p.xs[o] + static_cast<size_t>(c - p.bounds[o]) * p.ld;
 }
 
-// The row kernels run as programmatic dependents of the hub kernel (both in flight at once); a row
-// kernel block does not retire before the hub kernel has completed and flushed, so "row kernel
-// complete" implies "hub rows written" for whatever follows in the stream.
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // How the edge loop finds a neighbour row and its scale:
 //   kPlain   column_indices[e], then the dependent gathers nbr_scale[col] (* edge_scale[eid]);
 //   kParts   as kPlain, source matrix row-partitioned over peer GPUs (cold path, stg_agg_scaled_sum_parts_f32);
@@ -647,23 +642,6 @@ __global__ void __cluster_dims__(kHubCluster, 1, 1) __launch_bounds__(kHubThread
     }
     __syncthreads();                                // chunk_* are rewritten by the next iteration
   }
-}
-
-// Launch `kernel` so that it may start while the previous kernel of the stream is still running
-// (programmatic dependent launch); the kernel orders itself with grid_dependency_wait().
-template <typename... KArgs, typename... Args>
-cudaError_t launch_overlapped(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t stream, bool overlap,
-                              Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3(threads);
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = overlap ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // A/B switch while the pair form is being measured (STG_AGG_PAIR=0/1; read once).

@@ -81,4 +81,27 @@ __device__ __forceinline__ void add_vec(float& a, float b) { a += b; }
 __device__ __forceinline__ void add_vec(float2& a, float2 b) { a.x += b.x; a.y += b.y; }
 __device__ __forceinline__ void add_vec(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+// ---- programmatic dependent launch (hub kernel || row kernel) -----------------
+// The row kernels run as programmatic dependents of the hub kernel (both in flight at once); a row
+// kernel block does not retire before the hub kernel has completed and flushed, so "row kernel
+// complete" implies "hub rows written" for whatever follows in the stream.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch `kernel` so that it may start while the previous kernel of the stream is still running
+// (programmatic dependent launch); the kernel orders itself with grid_dependency_wait().
+template <typename... KArgs, typename... Args>
+cudaError_t launch_overlapped(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t stream, bool overlap,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace stg

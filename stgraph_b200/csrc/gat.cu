@@ -16,17 +16,21 @@
 // so one neighbour row is one coalesced (128-bit when D % 4 == 0) load; UNROLL neighbour rows are
 // loaded before any of them is consumed (the online-softmax update is applied per batch, so the
 // running max does not serialise the loads).  Rows longer than the view's hub threshold go to a
-// block-per-row kernel: 16 warps take strided batches and their (max, sum, acc) partials are merged
+// block-per-row kernel: 8 warps take strided batches and their (max, sum, acc) partials are merged
 // in a fixed order through shuffles + shared memory.
 // HBM-roofline kernels; algorithmic bytes: fwd 4*(2*N*H*D + 4*N*H + E + N+1),
 // bwd 4*(4*N*H*D + 6*N*H + 2*(E+N+1)).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
 namespace stg {
 namespace {
 
 constexpr int kGatThreads = 256;
-constexpr int kGatHubThreads = 512;
+constexpr int kGatHubThreads = 256;   // 8 warps per hub CTA: a 130-edge row has 5 batches, 16 warps would mostly wait at the barrier
 
 template <int VEC>
 __device__ __forceinline__ typename VecT<VEC>::type ldv(const float* p) {
@@ -99,7 +103,33 @@ __device__ __forceinline__ float head_sum(float v, int lph, unsigned gmask, int 
   return v;
 }
 
-template <int NACC> struct UnrollFor { static constexpr int value = NACC >= 4 ? 2 : 4; };
+// neighbour rows in flight per lane: a row of n edges costs n / U dependent L2 round trips, and on a power-law
+// graph the longest rows set the kernel time (config 3: 0.40 -> see profiles/r01_results.md)
+template <int NACC> struct UnrollFor { static constexpr int value = NACC >= 4 ? 2 : (NACC == 2 ? 4 : 8); };
+// the backward passes carry four per-edge scalars next to each neighbour row: 8 in flight would cost occupancy
+template <int NACC> struct UnrollBwd { static constexpr int value = NACC >= 4 ? 2 : 4; };
+
+// Calls body(integral_constant<G>, j) over [0, n) with G = U for every full group and exact powers of two for the tail.
+template <int U, class Body>
+__device__ __forceinline__ void for_exact_groups(int n, Body&& body) {
+  int j = 0;
+  for (; j + U <= n; j += U) body(std::integral_constant<int, U>{}, j);
+  if constexpr (U >= 8) {
+    if (j + 4 <= n) {
+      body(std::integral_constant<int, 4>{}, j);
+      j += 4;
+    }
+  }
+  if constexpr (U >= 4) {
+    if (j + 2 <= n) {
+      body(std::integral_constant<int, 2>{}, j);
+      j += 2;
+    }
+  }
+  if constexpr (U >= 2) {
+    if (j < n) body(std::integral_constant<int, 1>{}, j);
+  }
+}
 
 // ---------------------------------------------------------------------------------- forward
 template <int VEC, int GROUP, int NACC>
@@ -130,27 +160,35 @@ struct FwdState {
 template <int VEC, int GROUP, int NACC>
 __device__ __forceinline__ void gat_fwd_edges(const GatParams& p, const Lanes<VEC, GROUP, NACC>& L, int row, int beg,
                                               int end, int first_batch, int batch_step,
-                                              FwdState<VEC, GROUP, NACC>& st) {
+                                              FwdState<VEC, GROUP, NACC>& st, int nx_c) {
   using T = typename VecT<VEC>::type;
   constexpr int U = UnrollFor<NACC>::value;
   float erk[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) erk[k] = L.act[k] ? __ldg(p.er + static_cast<size_t>(row) * p.heads + L.hk[k]) : 0.f;
-  for (int base = beg + first_batch * GROUP; base < end; base += batch_step * GROUP) {
+  int base = beg + first_batch * GROUP;
+  for (; base < end; base += batch_step * GROUP) {
     const int n = min(GROUP, end - base);
-    const int my_c = (L.gl < n) ? ld_stream(p.col + base + L.gl) : 0;
-    for (int j = 0; j < n; j += U) {
-      float sc[U][NACC];
-      T v[U][NACC];
+    const int my_c = nx_c;
+    {                                             // column indices of the next batch, one batch ahead
+      const int nb = base + batch_step * GROUP + L.gl;
+      nx_c = (nb < end) ? ld_stream(p.col + nb) : 0;
+    }
+    // Exactly-sized groups (8, then 4 / 2 / 1 for the tail): no padding edges, so no per-edge predicates, and a
+    // 3-edge row costs 3 edges of instructions, not 8 (most rows of a power-law graph are that short: the row
+    // kernel was issue-bound at 545 warp instructions per row, profiles/r01_results.md).
+    auto group = [&](auto uu, int j) {
+      constexpr int UU = decltype(uu)::value;
+      float sc[UU][NACC];
+      T v[UU][NACC];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int c = __shfl_sync(L.gmask, my_c, min(j + u, GROUP - 1), GROUP);
-        const bool valid = (j + u) < n;
+      for (int u = 0; u < UU; ++u) {
+        const int c = __shfl_sync(L.gmask, my_c, j + u, GROUP);
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
           sc[u][k] = -INFINITY;
           zero_vec(v[u][k]);
-          if (valid && L.act[k]) {
+          if (L.act[k]) {
             sc[u][k] = lrelu(__ldg(p.el + static_cast<size_t>(c) * p.heads + L.hk[k]) + erk[k], p.slope);
             v[u][k] = ldv<VEC>(p.feat + static_cast<size_t>(c) * p.hd + L.off[k]);
           }
@@ -161,22 +199,30 @@ __device__ __forceinline__ void gat_fwd_edges(const GatParams& p, const Lanes<VE
         if (!L.act[k]) continue;
         float mb = sc[0][k];
 #pragma unroll
-        for (int u = 1; u < U; ++u) mb = fmaxf(mb, sc[u][k]);
+        for (int u = 1; u < UU; ++u) mb = fmaxf(mb, sc[u][k]);
         if (mb > st.m[k]) {                       // new running max: rescale what has been accumulated
-          const float r = __expf(st.m[k] - mb);   // exp(-inf) = 0 on the first batch
+          const float r = __expf(st.m[k] - mb);   // exp(-inf) = 0 on the first group
           st.s[k] *= r;
           scale_vec(st.acc[k], r);
           st.m[k] = mb;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float pe = expf(sc[u][k] - st.m[k]);   // exp(-inf) = 0 for padding edges
+        for (int u = 0; u < UU; ++u) {
+          const float pe = __expf(sc[u][k] - st.m[k]);
           st.s[k] += pe;
           fma_vec(st.acc[k], pe, v[u][k]);
         }
       }
-    }
+    };
+    for_exact_groups<U>(n, group);
   }
+}
+
+// columns of the first batch a lane group visits (the pipelined kernels load them one row ahead instead)
+template <int GROUP>
+__device__ __forceinline__ int first_cols(const GatParams& p, int beg, int end, int first_batch, int gl) {
+  const int e = beg + first_batch * GROUP + gl;
+  return (e < end) ? ld_stream(p.col + e) : 0;
 }
 
 template <int VEC, int GROUP, int NACC>
@@ -201,61 +247,16 @@ __global__ void __launch_bounds__(kGatThreads) gat_fwd_kernel(const GatParams p)
   L.init(p);
   const int warp = blockIdx.x * (kGatThreads / 32) + (threadIdx.x >> 5);
   const int row = warp * (32 / GROUP) + (threadIdx.x & 31) / GROUP;
-  if (row >= p.num_rows) return;
-  const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
-  if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) return;   // hub kernel owns this row
-  FwdState<VEC, GROUP, NACC> st;
-  st.init();
-  gat_fwd_edges<VEC, GROUP, NACC>(p, L, row, beg, end, 0, 1, st);
-  gat_fwd_store<VEC, GROUP, NACC>(p, L, row, end > beg, st);
-}
-
-template <int VEC, int GROUP, int NACC>
-__global__ void __launch_bounds__(kGatHubThreads) gat_fwd_hub_kernel(const GatParams p) {
-  using T = typename VecT<VEC>::type;
-  constexpr int WARPS = kGatHubThreads / 32;
-  constexpr int GPW = 32 / GROUP;
-  __shared__ T s_acc[WARPS][GROUP * NACC];
-  __shared__ float s_m[WARPS][GROUP * NACC], s_s[WARPS][GROUP * NACC];
-  Lanes<VEC, GROUP, NACC> L;
-  L.init(p);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n_hub = min(__ldg(p.hub_count), p.hub_capacity);
-  for (int i = blockIdx.x; i < n_hub; i += gridDim.x) {
-    const int row = __ldg(p.hub_rows + i);
+  if (row < p.num_rows) {
     const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
-    FwdState<VEC, GROUP, NACC> st;
-    st.init();
-    gat_fwd_edges<VEC, GROUP, NACC>(p, L, row, beg, end, wid * GPW + lane / GROUP, WARPS * GPW, st);
-    // groups of one warp -> lanes [0, GROUP)
-#pragma unroll
-    for (int o = GROUP; o < 32; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, st.m[k], o);
-        const float s2 = __shfl_xor_sync(0xffffffffu, st.s[k], o);
-        const T a2 = shfl_xor_t(0xffffffffu, st.acc[k], o);
-        st.merge(k, m2, s2, a2);
-      }
-    }
-    if (lane < GROUP) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        s_acc[wid][k * GROUP + lane] = st.acc[k];
-        s_m[wid][k * GROUP + lane] = st.m[k];
-        s_s[wid][k * GROUP + lane] = st.s[k];
-      }
-    }
-    __syncthreads();
-    if (wid == 0 && lane < GROUP) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k)
-        for (int w = 1; w < WARPS; ++w)
-          st.merge(k, s_m[w][k * GROUP + lane], s_s[w][k * GROUP + lane], s_acc[w][k * GROUP + lane]);
+    if (!(p.hub_threshold > 0 && (end - beg) > p.hub_threshold)) {   // else: the hub kernel owns this row
+      FwdState<VEC, GROUP, NACC> st;
+      st.init();
+      gat_fwd_edges<VEC, GROUP, NACC>(p, L, row, beg, end, 0, 1, st, first_cols<GROUP>(p, beg, end, 0, L.gl));
       gat_fwd_store<VEC, GROUP, NACC>(p, L, row, end > beg, st);
     }
-    __syncthreads();
   }
+  grid_dependency_wait();
 }
 
 // --------------------------------------------------------------------------------- backward
@@ -302,25 +303,31 @@ __device__ __forceinline__ void gat_bwd_prologue(const GatParams& p, const Lanes
 
 template <int VEC, int GROUP, int NACC, bool SRC_PARALLEL>
 __device__ __forceinline__ void gat_bwd_edges(const GatParams& p, const Lanes<VEC, GROUP, NACC>& L, int beg, int end,
-                                              int first_batch, int batch_step, BwdState<VEC, GROUP, NACC>& st) {
+                                              int first_batch, int batch_step, BwdState<VEC, GROUP, NACC>& st,
+                                              int nx_c) {
   using T = typename VecT<VEC>::type;
-  constexpr int U = UnrollFor<NACC>::value;
-  for (int base = beg + first_batch * GROUP; base < end; base += batch_step * GROUP) {
+  constexpr int U = UnrollBwd<NACC>::value;
+  int base = beg + first_batch * GROUP;
+  for (; base < end; base += batch_step * GROUP) {
     const int n = min(GROUP, end - base);
-    const int my_c = (L.gl < n) ? ld_stream(p.col + base + L.gl) : 0;
-    for (int j = 0; j < n; j += U) {
-      T nb[U][NACC];
-      float pre[U][NACC], mm[U][NACC], inv[U][NACC], dt[U][NACC];
+    const int my_c = nx_c;
+    {                                             // column indices of the next batch, one batch ahead
+      const int nxb = base + batch_step * GROUP + L.gl;
+      nx_c = (nxb < end) ? ld_stream(p.col + nxb) : 0;
+    }
+    auto group = [&](auto uu, int j) {          // exactly-sized groups, see gat_fwd_edges
+      constexpr int UU = decltype(uu)::value;
+      T nb[UU][NACC];
+      float pre[UU][NACC], mm[UU][NACC], inv[UU][NACC], dt[UU][NACC];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int c = __shfl_sync(L.gmask, my_c, min(j + u, GROUP - 1), GROUP);
+      for (int u = 0; u < UU; ++u) {
+        const int c = __shfl_sync(L.gmask, my_c, j + u, GROUP);
         const size_t ch = static_cast<size_t>(c) * p.heads;
-        const bool valid = (j + u) < n;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
           zero_vec(nb[u][k]);
           pre[u][k] = mm[u][k] = inv[u][k] = dt[u][k] = 0.f;
-          if (valid && L.act[k]) {
+          if (L.act[k]) {
             if (SRC_PARALLEL) {      // neighbour = destination: its er, max, sum, dot, dout row
               nb[u][k] = ldv<VEC>(p.gout + static_cast<size_t>(c) * p.hd + L.off[k]);
               pre[u][k] = st.c_a[k] + __ldg(p.er + ch + L.hk[k]);
@@ -339,21 +346,21 @@ __device__ __forceinline__ void gat_bwd_edges(const GatParams& p, const Lanes<VE
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool valid = (j + u) < n;
+      for (int u = 0; u < UU; ++u) {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
           const float part = L.act[k] ? dotv(st.cen[k], nb[u][k]) : 0.f;
           const float dalpha = head_sum(part, p.lph, L.gmask, GROUP);      // <dout[v,h,:], feat[u,h,:]>
-          if (valid && L.act[k]) {
-            const float alpha = expf(lrelu(pre[u][k], p.slope) - mm[u][k]) * inv[u][k];
+          if (L.act[k]) {
+            const float alpha = __expf(lrelu(pre[u][k], p.slope) - mm[u][k]) * inv[u][k];
             const float g = alpha * (dalpha - dt[u][k]) * (pre[u][k] > 0.f ? 1.f : p.slope);
             st.acch[k] += g;
             if (SRC_PARALLEL) fma_vec(st.accv[k], alpha, nb[u][k]);
           }
         }
       }
-    }
+    };
+    for_exact_groups<U>(n, group);
   }
 }
 
@@ -375,59 +382,245 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(const GatParams p)
   L.init(p);
   const int warp = blockIdx.x * (kGatThreads / 32) + (threadIdx.x >> 5);
   const int row = warp * (32 / GROUP) + (threadIdx.x & 31) / GROUP;
-  if (row >= p.num_rows) return;
-  const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
-  if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) return;
-  BwdState<VEC, GROUP, NACC> st;
-  gat_bwd_prologue<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st, true);
-  gat_bwd_edges<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, beg, end, 0, 1, st);
-  gat_bwd_store<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st);
+  if (row < p.num_rows) {
+    const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
+    if (!(p.hub_threshold > 0 && (end - beg) > p.hub_threshold)) {
+      BwdState<VEC, GROUP, NACC> st;
+      gat_bwd_prologue<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st, true);
+      gat_bwd_edges<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, beg, end, 0, 1, st, first_cols<GROUP>(p, beg, end, 0, L.gl));
+      gat_bwd_store<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st);
+    }
+  }
+  grid_dependency_wait();
 }
 
-template <int VEC, int GROUP, int NACC, bool SRC_PARALLEL>
-__global__ void __launch_bounds__(kGatHubThreads) gat_bwd_hub_kernel(const GatParams p) {
+
+// Hub rows (longer than the view's hub threshold) in two tiers, for all three passes (KIND as above):
+//   * a row of up to kGatGiantEdges edges is walked by ONE CTA: its 8 warps take strided batches and merge their
+//     partials (forward: online-softmax states (max, sum, acc); backward: plain sums) through shuffles and
+//     shared memory;
+//   * a longer row is walked by a whole thread-block cluster (8 CTAs, 64 warps) and the leader CTA merges the
+//     CTA partials over distributed shared memory -- one CTA needs ~100 us of dependent L2 round trips for the
+//     8.5 K-edge rows of config 3, which used to be the critical path of every pass.
+// Every merge runs in a fixed order: deterministic, no atomics, no scratch in HBM.  Entry i of the hub list
+// is tested by cluster i % n_clusters (giant?) and by CTA i % n_ctas (not giant?), so the list may be in any
+// order; StaticGraph sorts it by length so that the giant rows start first, one per cluster.
+constexpr int kGatCluster = 8;
+constexpr int kGatGiantEdges = 1024;
+
+template <int NACC> struct HubThreads { static constexpr int value = NACC >= 4 ? kGatHubThreads / 2 : kGatHubThreads; };
+
+template <int VEC, int GROUP, int NACC, int KIND>
+__global__ void __cluster_dims__(kGatCluster, 1, 1) __launch_bounds__(HubThreads<NACC>::value, NACC == 1 ? 4 : 1)
+    gat_hub_kernel(const GatParams p) {
   using T = typename VecT<VEC>::type;
-  constexpr int WARPS = kGatHubThreads / 32;
+  namespace cg = cooperative_groups;
+  constexpr int WARPS = HubThreads<NACC>::value / 32;
   constexpr int GPW = 32 / GROUP;
+  constexpr bool FWD = KIND == 0;
+  constexpr bool SRC = KIND == 2;
   __shared__ T s_v[WARPS][GROUP * NACC];
-  __shared__ float s_h[WARPS][GROUP * NACC];
+  __shared__ float s_a[WARPS][GROUP * NACC], s_b[FWD ? WARPS : 1][GROUP * NACC];
+  __shared__ T c_v[GROUP * NACC];                       // this CTA's partial, read by the cluster leader
+  __shared__ float c_a[GROUP * NACC], c_b[GROUP * NACC];
+  // the row kernel is launched behind this one as a programmatic dependent: the two write disjoint rows
+  asm volatile("griddepcontrol.launch_dependents;");
+  cg::cluster_group cluster = cg::this_cluster();
   Lanes<VEC, GROUP, NACC> L;
   L.init(p);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int crank = static_cast<int>(cluster.block_rank());
   const int n_hub = min(__ldg(p.hub_count), p.hub_capacity);
+  const bool leader_lanes = wid == 0 && lane < GROUP;
+
+  // Walk edges [beg,end) of `row` with `slots` cooperating (warp, group) slots, this thread's being `slot`; merge the
+  // CTA's partials into warp 0, lanes [0, GROUP) (registers `st`) in a fixed order.
+  using State = typename std::conditional<FWD, FwdState<VEC, GROUP, NACC>, BwdState<VEC, GROUP, NACC>>::type;
+  State st;
+  auto cta_partial = [&](int row, int beg, int end, int slot, int slots, bool write_dot) {
+    const int c_first = first_cols<GROUP>(p, beg, end, slot, L.gl);
+    if constexpr (FWD) {
+      st.init();
+      gat_fwd_edges<VEC, GROUP, NACC>(p, L, row, beg, end, slot, slots, st, c_first);
+#pragma unroll
+      for (int o = GROUP; o < 32; o <<= 1) {            // groups of one warp -> lanes [0, GROUP)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          const float m2 = __shfl_xor_sync(0xffffffffu, st.m[k], o);
+          const float s2 = __shfl_xor_sync(0xffffffffu, st.s[k], o);
+          const T a2 = shfl_xor_t(0xffffffffu, st.acc[k], o);
+          st.merge(k, m2, s2, a2);
+        }
+      }
+      if (lane < GROUP) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          s_v[wid][k * GROUP + lane] = st.acc[k];
+          s_a[wid][k * GROUP + lane] = st.m[k];
+          s_b[wid][k * GROUP + lane] = st.s[k];
+        }
+      }
+      __syncthreads();
+      if (leader_lanes) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+          for (int w = 1; w < WARPS; ++w)
+            st.merge(k, s_a[w][k * GROUP + lane], s_b[w][k * GROUP + lane], s_v[w][k * GROUP + lane]);
+      }
+    } else {
+      gat_bwd_prologue<VEC, GROUP, NACC, SRC>(p, L, row, st, write_dot && leader_lanes);
+      gat_bwd_edges<VEC, GROUP, NACC, SRC>(p, L, beg, end, slot, slots, st, c_first);
+#pragma unroll
+      for (int o = GROUP; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          st.acch[k] += __shfl_xor_sync(0xffffffffu, st.acch[k], o);
+          add_vec(st.accv[k], shfl_xor_t(0xffffffffu, st.accv[k], o));
+        }
+      }
+      if (lane < GROUP) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          s_v[wid][k * GROUP + lane] = st.accv[k];
+          s_a[wid][k * GROUP + lane] = st.acch[k];
+        }
+      }
+      __syncthreads();
+      if (leader_lanes) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+          for (int w = 1; w < WARPS; ++w) {
+            add_vec(st.accv[k], s_v[w][k * GROUP + lane]);
+            st.acch[k] += s_a[w][k * GROUP + lane];
+          }
+      }
+    }
+  };
+  auto store_row = [&](int row, bool nonempty) {         // warp 0, lanes [0, GROUP)
+    if constexpr (FWD) gat_fwd_store<VEC, GROUP, NACC>(p, L, row, nonempty, st);
+    else gat_bwd_store<VEC, GROUP, NACC, SRC>(p, L, row, st);
+  };
+
+  // tier 2: giant rows, one per cluster at a time (the same decisions in every CTA of the cluster)
+  const int cluster_id = blockIdx.x / kGatCluster, n_clusters = gridDim.x / kGatCluster;
+  for (int i = cluster_id; i < n_hub; i += n_clusters) {
+    const int row = __ldg(p.hub_rows + i);
+    const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
+    if ((end - beg) <= kGatGiantEdges) continue;
+    cta_partial(row, beg, end, (crank * WARPS + wid) * GPW + lane / GROUP, kGatCluster * WARPS * GPW, crank == 0);
+    if (leader_lanes) {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        if constexpr (FWD) {
+          c_v[k * GROUP + lane] = st.acc[k];
+          c_a[k * GROUP + lane] = st.m[k];
+          c_b[k * GROUP + lane] = st.s[k];
+        } else {
+          c_v[k * GROUP + lane] = st.accv[k];
+          c_a[k * GROUP + lane] = st.acch[k];
+        }
+      }
+    }
+    cluster.sync();                                      // every CTA's partial is in its c_* arrays
+    if (crank == 0 && leader_lanes) {                    // CTAs of the cluster, fixed order, over DSMEM
+      for (int c = 1; c < kGatCluster; ++c) {
+        const T* rv = cluster.map_shared_rank(c_v, c);
+        const float* ra = cluster.map_shared_rank(c_a, c);
+        const float* rb = cluster.map_shared_rank(c_b, c);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          if constexpr (FWD) {
+            st.merge(k, ra[k * GROUP + lane], rb[k * GROUP + lane], rv[k * GROUP + lane]);
+          } else {
+            add_vec(st.accv[k], rv[k * GROUP + lane]);
+            st.acch[k] += ra[k * GROUP + lane];
+          }
+        }
+      }
+      store_row(row, true);
+    }
+    cluster.sync();                                      // peers keep c_* alive until the leader has read them
+  }
+  // tier 1: the other hub rows, one per CTA at a time
   for (int i = blockIdx.x; i < n_hub; i += gridDim.x) {
     const int row = __ldg(p.hub_rows + i);
     const int beg = __ldg(p.row_off + row), end = __ldg(p.row_off + row + 1);
-    BwdState<VEC, GROUP, NACC> st;
-    gat_bwd_prologue<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st, wid == 0 && lane < GROUP);
-    gat_bwd_edges<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, beg, end, wid * GPW + lane / GROUP, WARPS * GPW, st);
-#pragma unroll
-    for (int o = GROUP; o < 32; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        st.acch[k] += __shfl_xor_sync(0xffffffffu, st.acch[k], o);
-        add_vec(st.accv[k], shfl_xor_t(0xffffffffu, st.accv[k], o));
-      }
-    }
-    if (lane < GROUP) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        s_v[wid][k * GROUP + lane] = st.accv[k];
-        s_h[wid][k * GROUP + lane] = st.acch[k];
-      }
-    }
-    __syncthreads();
-    if (wid == 0 && lane < GROUP) {
-#pragma unroll
-      for (int k = 0; k < NACC; ++k)
-        for (int w = 1; w < WARPS; ++w) {
-          add_vec(st.accv[k], s_v[w][k * GROUP + lane]);
-          st.acch[k] += s_h[w][k * GROUP + lane];
-        }
-      gat_bwd_store<VEC, GROUP, NACC, SRC_PARALLEL>(p, L, row, st);
-    }
-    __syncthreads();
+    if ((end - beg) > kGatGiantEdges) continue;
+    cta_partial(row, beg, end, wid * GPW + lane / GROUP, WARPS * GPW, true);
+    if (leader_lanes) store_row(row, end > beg);
+    __syncthreads();                                     // s_* are rewritten by the next row
   }
+}
+
+// Row-queue form of the three row kernels for one row per warp (GROUP = 32).  On a power-law graph most rows
+// hold a handful of edges, so a one-row-per-warp grid is a string of dependent L2 round trips per block
+// (row_offset -> column -> neighbour rows -> store) plus one block launch per 8 rows.  Here a block owns
+// rows_per_block consecutive rows, its warps draw rows from a shared-memory counter, and the row_offset pair of
+// the row after next and the first column batch of the next row are in flight while a row is processed.
+// KIND: 0 forward, 1 backward pass A (destination-parallel), 2 backward pass B (source-parallel).
+constexpr int kGatRowsPerWarp = 16;
+
+template <int VEC, int NACC, int KIND>
+__global__ void __launch_bounds__(kGatThreads, NACC == 1 ? 4 : 1) gat_rows_pipe_kernel(const GatParams p, int rows_per_block) {
+  constexpr int GROUP = 32;
+  __shared__ int next_row;
+  Lanes<VEC, GROUP, NACC> L;
+  L.init(p);
+  const int lane = threadIdx.x & 31;
+  const int first = blockIdx.x * rows_per_block;
+  const int last = min(first + rows_per_block, p.num_rows);
+  if (threadIdx.x == 0) next_row = first;
+  __syncthreads();
+  auto draw = [&]() {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&next_row, 1);
+    return __shfl_sync(0xffffffffu, r, 0);
+  };
+  auto offsets = [&](int row, int& beg, int& end) {      // end = -1: nothing to do (past the end)
+    beg = 0;
+    end = -1;
+    if (row < last) {
+      beg = __ldg(p.row_off + row);
+      end = __ldg(p.row_off + row + 1);
+    }
+  };
+  auto drop_hub = [&](int& beg, int& end) {              // hub rows belong to the block-per-row kernel
+    if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) beg = 0, end = -1;
+  };
+  int row0 = draw();
+  if (row0 >= last) {
+    grid_dependency_wait();
+    return;
+  }
+  int beg0, end0, beg1, end1;
+  offsets(row0, beg0, end0);
+  int row1 = draw();
+  offsets(row1, beg1, end1);
+  drop_hub(beg0, end0);
+  int c0 = first_cols<GROUP>(p, beg0, end0, 0, lane);
+  while (row0 < last) {
+    const int row2 = draw();
+    int beg2, end2;
+    offsets(row2, beg2, end2);
+    drop_hub(beg1, end1);
+    const int c1 = first_cols<GROUP>(p, beg1, end1, 0, lane);
+    if (end0 >= 0) {
+      if constexpr (KIND == 0) {
+        FwdState<VEC, GROUP, NACC> st;
+        st.init();
+        gat_fwd_edges<VEC, GROUP, NACC>(p, L, row0, beg0, end0, 0, 1, st, c0);
+        gat_fwd_store<VEC, GROUP, NACC>(p, L, row0, end0 > beg0, st);
+      } else {
+        BwdState<VEC, GROUP, NACC> st;
+        gat_bwd_prologue<VEC, GROUP, NACC, KIND == 2>(p, L, row0, st, true);
+        gat_bwd_edges<VEC, GROUP, NACC, KIND == 2>(p, L, beg0, end0, 0, 1, st, c0);
+        gat_bwd_store<VEC, GROUP, NACC, KIND == 2>(p, L, row0, st);
+      }
+    }
+    row0 = row1; beg0 = beg1; end0 = end1; c0 = c1;
+    row1 = row2; beg1 = beg2; end1 = end2;
+  }
+  grid_dependency_wait();
 }
 
 template <int VEC, int GROUP, int NACC>
@@ -436,17 +629,29 @@ int launch_gat(const GatParams& p, int which, cudaStream_t s) {
   const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
   if (blocks <= 0) return STG_OK;
   const bool hubs = p.hub_threshold > 0 && p.hub_rows != nullptr;
-  const int hub_grid = 2 * sm_count();
-  if (which == 0) {
-    gat_fwd_kernel<VEC, GROUP, NACC><<<blocks, kGatThreads, 0, s>>>(p);
-    if (hubs) gat_fwd_hub_kernel<VEC, GROUP, NACC><<<hub_grid, kGatHubThreads, 0, s>>>(p);
-  } else if (which == 1) {
-    gat_bwd_kernel<VEC, GROUP, NACC, false><<<blocks, kGatThreads, 0, s>>>(p);
-    if (hubs) gat_bwd_hub_kernel<VEC, GROUP, NACC, false><<<hub_grid, kGatHubThreads, 0, s>>>(p);
-  } else {
-    gat_bwd_kernel<VEC, GROUP, NACC, true><<<blocks, kGatThreads, 0, s>>>(p);
-    if (hubs) gat_bwd_hub_kernel<VEC, GROUP, NACC, true><<<hub_grid, kGatHubThreads, 0, s>>>(p);
+  const int hub_grid = 4 * (sm_count() / kGatCluster) * kGatCluster;   // 8-warp CTAs, <= 64 registers: 4 per SM leave half an SM to the row kernel
+  // Hub rows first: the longest rows are the critical path, the row kernel fills the SMs they leave idle.
+  if (hubs) {
+    constexpr int ht = HubThreads<NACC>::value;
+    if (which == 0) gat_hub_kernel<VEC, GROUP, NACC, 0><<<hub_grid, ht, 0, s>>>(p);
+    else if (which == 1) gat_hub_kernel<VEC, GROUP, NACC, 1><<<hub_grid, ht, 0, s>>>(p);
+    else gat_hub_kernel<VEC, GROUP, NACC, 2><<<hub_grid, ht, 0, s>>>(p);
+    STG_LAUNCH_CHECK("gat hub kernel");
   }
+  if constexpr (GROUP == 32) {
+    if (p.num_rows >= 4096) {      // the queue pays off once there are several blocks per SM
+      const int rpb = (kGatThreads / 32) * kGatRowsPerWarp;
+      const int pblocks = (p.num_rows + rpb - 1) / rpb;
+      if (which == 0) STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 0>, pblocks, kGatThreads, s, hubs, p, rpb));
+      else if (which == 1) STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 1>, pblocks, kGatThreads, s, hubs, p, rpb));
+      else STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 2>, pblocks, kGatThreads, s, hubs, p, rpb));
+      STG_LAUNCH_CHECK("gat rows (queue) kernel");
+      return STG_OK;
+    }
+  }
+  if (which == 0) gat_fwd_kernel<VEC, GROUP, NACC><<<blocks, kGatThreads, 0, s>>>(p);
+  else if (which == 1) gat_bwd_kernel<VEC, GROUP, NACC, false><<<blocks, kGatThreads, 0, s>>>(p);
+  else gat_bwd_kernel<VEC, GROUP, NACC, true><<<blocks, kGatThreads, 0, s>>>(p);
   STG_LAUNCH_CHECK("gat kernel");
   return STG_OK;
 }

@@ -148,9 +148,11 @@ class CSR:
         _lib.call("stg_csr_hub_rows", self.row_offset.data_ptr(), n, HUB_THRESHOLD, self._hub_rows.data_ptr(),
                   cap, self._hub_count.data_ptr(), _lib.current_stream_ptr())
         self._hub_enabled = True
+        self._hub_sync = sync
         if sync:
             self._hub_enabled = int(self._hub_count.item()) > 0
         self._view = None
+        self._alt_views = {}
 
     def view(self) -> _lib.StgCsrView:
         if self._view is None:
@@ -175,6 +177,47 @@ class CSR:
                 v.hub_capacity = 0
             self._view = v
         return self._view
+
+
+def _alt_view(self, threshold: int) -> _lib.StgCsrView:
+    """The same CSR with a hub-row list for another threshold (the attention kernels split rows much earlier than
+    the plain sum: their per-edge work is a longer dependent chain, ``ops_gat.GAT_HUB_THRESHOLD``).  Cached."""
+    threshold = int(threshold)
+    if threshold <= 0 or threshold == HUB_THRESHOLD:
+        return self.view()
+    alt = getattr(self, "_alt_views", None)
+    if alt is None:
+        alt = self._alt_views = {}
+    if threshold not in alt:
+        base = self.view()
+        n, e = self.num_nodes, self.num_edges
+        cap = e // threshold + 1
+        dev = self.row_offset.device
+        rows = torch.empty(cap, dtype=torch.int32, device=dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("stg_csr_hub_rows", self.row_offset.data_ptr(), n, threshold, rows.data_ptr(), cap, count.data_ptr(),
+                  _lib.current_stream_ptr())
+        enabled = True
+        if getattr(self, "_hub_sync", False):      # static graph: one read-back, skip the launch when there are none
+            cnt = min(int(count.item()), cap)
+            enabled = cnt > 0
+            if cnt > 1:     # longest rows first: blocks take the list round-robin, so the big rows start at once
+                r = rows[:cnt].long()
+                length = (self.row_offset[r + 1] - self.row_offset[r]).long()
+                order = torch.sort(length * self.num_nodes + (self.num_nodes - 1 - r), descending=True).indices
+                rows[:cnt] = rows[:cnt][order]
+        v = _lib.StgCsrView()
+        for name, _ in _lib.StgCsrView._fields_:
+            setattr(v, name, getattr(base, name))
+        v.hub_rows = rows.data_ptr() if enabled else None
+        v.hub_count = count.data_ptr() if enabled else None
+        v.hub_threshold = threshold if enabled else 0
+        v.hub_capacity = cap if enabled else 0
+        alt[threshold] = (v, rows, count)
+    return alt[threshold][0]
+
+
+CSR.view_with_hub_threshold = _alt_view
 
 
 def build_csr_pair(src: torch.Tensor, dst: torch.Tensor, num_nodes: int, want_perm: bool = False):

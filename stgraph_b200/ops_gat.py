@@ -10,7 +10,24 @@ import ctypes
 
 import torch
 
+import os
+
 from . import _lib, kernels
+
+#: rows longer than this go to the block-per-row attention kernels (the plain sum splits at csr.HUB_THRESHOLD = 1024).
+#: A warp walks a row in groups of 8 (forward) / 4 (backward) neighbour rows per L2 round trip, so on a power-law graph
+#: the longest warp-owned row sets the kernel time: config 3 (arxiv shape), 1024 -> 128 (profiles/r01_results.md).
+GAT_HUB_THRESHOLD = int(os.environ.get("STG_GAT_HUB_THRESHOLD", "128"))
+
+
+def _views(graph):
+    """(in-edge view, out-edge view) of ``graph`` with the attention kernels' hub threshold."""
+    bwd = graph.bwd_view()            # backward first: a dynamic graph builds both views in one go
+    fwd = graph.fwd_view()
+    f, b = graph._forward_graph, graph._backward_graph
+    if hasattr(f, "view_with_hub_threshold") and hasattr(b, "view_with_hub_threshold"):
+        return f.view_with_hub_threshold(GAT_HUB_THRESHOLD), b.view_with_hub_threshold(GAT_HUB_THRESHOLD)
+    return fwd, bwd
 
 
 class _GatEdgeSoftmax(torch.autograd.Function):
@@ -23,7 +40,7 @@ class _GatEdgeSoftmax(torch.autograd.Function):
         out = torch.empty_like(feat)
         row_max = torch.empty(n, h, device=feat.device, dtype=torch.float32)
         row_sum = torch.empty_like(row_max)
-        _lib.call("stg_gat_softmax_fwd_f32", ctypes.byref(graph.fwd_view()), el2.data_ptr(), er2.data_ptr(),
+        _lib.call("stg_gat_softmax_fwd_f32", ctypes.byref(_views(graph)[0]), el2.data_ptr(), er2.data_ptr(),
                   feat.data_ptr(), h, d, float(slope), out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(),
                   _lib.current_stream_ptr())
         kernels.launch_count += 1
@@ -44,7 +61,8 @@ class _GatEdgeSoftmax(torch.autograd.Function):
         d_el = torch.empty_like(el2)
         d_er = torch.empty_like(er2)
         dot = torch.empty_like(el2)
-        _lib.call("stg_gat_softmax_bwd_f32", ctypes.byref(g.fwd_view()), ctypes.byref(g.bwd_view()), el2.data_ptr(),
+        vf, vb = _views(g)
+        _lib.call("stg_gat_softmax_bwd_f32", ctypes.byref(vf), ctypes.byref(vb), el2.data_ptr(),
                   er2.data_ptr(), feat.data_ptr(), out.data_ptr(), gout.data_ptr(), row_max.data_ptr(),
                   row_sum.data_ptr(), h, d, ctx.slope, d_feat.data_ptr(), d_el.data_ptr(), d_er.data_ptr(),
                   dot.data_ptr(), _lib.current_stream_ptr())
