@@ -26,7 +26,11 @@ What it restates (citations are relative to ``/root/reference``):
 Parity pinning status: the reference ships no numeric tests for this path
 (SURVEY.md section 4), so the oracle is pinned against *outputs of the reference
 itself run in the build container*: its CSR builder (``csr.cu`` compiled from
-where it lies) and its generated CUDA kernels executed by the emulation shim.
+where it lies), its host-side PCSR (``pcsr.cu`` compiled from where it lies; fixtures
+``tests/golden/ref_pcsr.npz``) and its generated CUDA kernels executed by the emulation
+shim.  Still unpinned: GPMA (``gpma.cu`` needs CUDA dynamic parallelism v1, which does not
+exist for sm_100 -- SURVEY.md trap T4); its view contract is the same labelled view as PCSR's
+with ascending rows.
 The committed fixtures in ``tests/golden/`` were produced by
 ``oracle/make_golden.py``; see DESIGN.md "Oracle".
 """

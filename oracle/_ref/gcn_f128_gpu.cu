@@ -23,7 +23,7 @@ extern "C" __global__ void K14
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V103_tmp = 0;
-            int offset2 = dst_id * 128 + tx;int offset3 = dst_id * 1 + tx/128;
+            int offset2 = dst_id * 1 + tx/128;int offset3 = dst_id * 128 + tx;
             
             for (int e=beg;e<end;++e) {
                 
@@ -50,8 +50,8 @@ extern "C" __global__ void K14
             
             
             
-            float V104_tmp = V103_tmp*Vnormcen[offset3];
-            V104[offset2] = V104_tmp;
+            float V104_tmp = V103_tmp*Vnormcen[offset2];
+            V104[offset3] = V104_tmp;
             
         }
     }
@@ -86,11 +86,11 @@ extern "C" __global__ void K14
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = dst_id * 128 + tx;int offset1 = dst_id * 1 + tx/128;
+                int offset0 = dst_id * 1 + tx/128;int offset1 = dst_id * 128 + tx;
                 
                 
                 
-                float V106_tmp = V105[offset0]*Vnormcen[offset1];
+                float V106_tmp = V105[offset1]*Vnormcen[offset0];
                 
                 
                 

@@ -23,7 +23,7 @@ extern "C" __global__ void K0
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V1_tmp = 0;
-            int offset2 = dst_id * 16 + tx;int offset3 = dst_id * 1 + tx/16;
+            int offset2 = dst_id * 1 + tx/16;int offset3 = dst_id * 16 + tx;
             
             for (int e=beg;e<end;++e) {
                 
@@ -50,8 +50,8 @@ extern "C" __global__ void K0
             
             
             
-            float V2_tmp = V1_tmp*Vnormcen[offset3];
-            V2[offset2] = V2_tmp;
+            float V2_tmp = V1_tmp*Vnormcen[offset2];
+            V2[offset3] = V2_tmp;
             
         }
     }

@@ -23,7 +23,7 @@ extern "C" void K2
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V10_tmp = 0;
-            int offset3 = dst_id * 7 + tx;int offset4 = dst_id * 1 + tx/7;
+            int offset3 = dst_id * 1 + tx/7;int offset4 = dst_id * 7 + tx;
             
             for (int e=beg;e<end;++e) {
                 
@@ -54,8 +54,8 @@ extern "C" void K2
             
             
             
-            float V11_tmp = V10_tmp*Vnormcen[offset4];
-            V11[offset3] = V11_tmp;
+            float V11_tmp = V10_tmp*Vnormcen[offset3];
+            V11[offset4] = V11_tmp;
             
         }
     }

@@ -26,6 +26,69 @@ def make_graph(n=40, e=200, seed=0):
     return (key // n).astype(np.int32), (key % n).astype(np.int32)
 
 
+def dynamic_stream(n, t_count, base, churn, seed):
+    """Snapshot edge lists with churn, duplicates, one edge that is deleted and later re-added, and a near-empty step."""
+    rng = np.random.default_rng(seed)
+    cur = set()
+    while len(cur) < base:
+        a, b = rng.integers(0, n, 2)
+        if a != b:
+            cur.add((int(a), int(b)))
+    pinned = sorted(cur)[0]                       # deleted at t=1, re-added at t=3
+    snaps = []
+    for t in range(t_count):
+        now = set(cur)
+        if t in (1, 2):
+            now.discard(pinned)
+        else:
+            now.add(pinned)
+        if t == t_count - 2:
+            now = set(sorted(now)[:3])            # almost everything deleted at once, then re-inserted
+        lst = sorted(now)
+        rng.shuffle(lst)
+        snaps.append(lst + lst[: max(1, len(lst) // 10)])          # duplicates collapse (dynamic_graph.py:58-63)
+        curl = sorted(cur)
+        for i in rng.choice(len(curl), size=min(churn, len(curl)), replace=False):
+            cur.discard(curl[i])
+        while len(cur) < base:
+            a, b = rng.integers(0, n, 2)
+            if a != b:
+                cur.add((int(a), int(b)))
+    return snaps
+
+
+def make_pcsr_golden():
+    """Drive the reference's PCSR exactly like ``PCSRGraph`` does (forward roll over all timestamps, then the
+    backward roll ``_update_graph_backward`` T-1 -> 0) and record the CSR it builds at every stop."""
+    from oracle import structure as S
+
+    out = {}
+    for tag, (n, T, base, churn, seed) in {"a": (60, 7, 300, 40, 3), "b": (24, 6, 70, 25, 11)}.items():
+        snaps = dynamic_stream(n, T, base, churn, seed)
+        ups = S.snapshot_updates(snaps)
+        max_edges = len({e for s in snaps for e in s})
+        flat = np.array([e for s in snaps for e in s], dtype=np.int32).reshape(-1, 2)
+        out[f"{tag}/num_nodes"] = np.int32(n)
+        out[f"{tag}/snap_edges"] = flat
+        out[f"{tag}/snap_sizes"] = np.array([len(s) for s in snaps], dtype=np.int32)
+        ref = RE.RefPcsr(n, max_edges)
+        for t in range(T):
+            ref.step(ups[t]["add"], ups[t]["delete"])
+            for d, rev in (("fwd", False), ("bwd", True)):
+                ro, col, eid, nid, ind, outd = ref.build(rev)
+                out[f"{tag}/{d}/{t}/row_offset"], out[f"{tag}/{d}/{t}/column_indices"] = ro, col
+                out[f"{tag}/{d}/{t}/eids"], out[f"{tag}/{d}/{t}/node_ids"] = eid, nid
+                out[f"{tag}/{d}/{t}/pcsr_in_degrees"], out[f"{tag}/{d}/{t}/pcsr_out_degrees"] = ind, outd
+        for t in range(T - 1, 0, -1):             # pcsr_graph.py:146-166: add the deletions, delete the additions of t
+            ref.step(ups[t]["delete"], ups[t]["add"])
+            ro, col, eid, nid, _, _ = ref.build(True)
+            out[f"{tag}/rewind/{t - 1}/row_offset"], out[f"{tag}/rewind/{t - 1}/column_indices"] = ro, col
+            out[f"{tag}/rewind/{t - 1}/eids"] = eid
+        ref.close()
+    np.savez_compressed(os.path.join(GOLD, "ref_pcsr.npz"), **out)
+    print("wrote", os.path.join(GOLD, "ref_pcsr.npz"), len(out), "arrays")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     n, e = 40, 200
@@ -81,6 +144,7 @@ def main():
     for case, (hh, dd) in (("gat_h8d16", (8, 16)), ("gat_h2d4", (2, 4))):
         el, er, feat = f32(n, hh, 1), f32(n, hh, 1), f32(n, hh, dd)
         run_case(case, {"Velinb": el, "Vercen": er, "Vfeat_srcinb": feat}, [f32(n, hh, dd)])
+    make_pcsr_golden()
     np.savez_compressed(os.path.join(GOLD, "ref_kernels.npz"), **kout)
     print("wrote", os.path.join(GOLD, "ref_structure.npz"), "and ref_kernels.npz:", len(kout), "arrays")
 

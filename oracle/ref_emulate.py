@@ -100,3 +100,46 @@ def run_reference_kernel(lib, kernel, tensors, csr, num_nodes):
     fn(arr, ro.ctypes.data, ei.ctypes.data, ci.ctypes.data, ni.ctypes.data, num_nodes, max_dims[1], max_dims[0],
        group, npb, nblks, nthrs)
     return (nblks, nthrs, group, npb)
+
+
+class RefPcsr:
+    """The reference's host-side ``PCSR`` (``/root/reference/stgraph/graph/dynamic/pcsr/pcsr.cu:325-891``) driven the way
+    ``PCSRGraph`` drives it (``pcsr_graph.py:45-166``): ``edge_update_list(add, is_reverse_edge=True)``,
+    ``edge_update_list(delete, is_delete=True, is_reverse_edge=True)``, ``label_edges()``, then ``build_csr()``
+    (forward) or ``build_reverse_csr()`` (backward)."""
+
+    def __init__(self, num_nodes: int, max_edges: int):
+        lib = ctypes.CDLL(os.path.join(REF_DIR, "ref_pcsr.so"))
+        lib.ref_pcsr_new.restype = ctypes.c_void_p
+        lib.ref_pcsr_new.argtypes = [ctypes.c_int, ctypes.c_int]
+        lib.ref_pcsr_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.ref_pcsr_label.argtypes = [ctypes.c_void_p]
+        lib.ref_pcsr_build.restype = ctypes.c_int
+        lib.ref_pcsr_build.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        lib.ref_pcsr_free.argtypes = [ctypes.c_void_p]
+        self.lib, self.n, self.max_edges = lib, int(num_nodes), max(int(max_edges), 1)
+        self.h = lib.ref_pcsr_new(self.n, self.max_edges)
+
+    def update(self, src, dst, delete: bool):
+        s = np.ascontiguousarray(np.asarray(src, dtype=np.uint32))
+        d = np.ascontiguousarray(np.asarray(dst, dtype=np.uint32))
+        self.lib.ref_pcsr_update(self.h, s.ctypes.data, d.ctypes.data, int(s.shape[0]), int(delete), 1)
+
+    def step(self, add, delete):
+        """One ``_update_graph_forward`` (or, with the two lists swapped, ``_update_graph_backward``)."""
+        self.update(add[0], add[1], False)
+        self.update(delete[0], delete[1], True)
+        self.lib.ref_pcsr_label(self.h)
+
+    def build(self, reverse: bool):
+        """(row_offset, column_indices, eids, node_ids, in_degrees, out_degrees) as the reference fills them."""
+        n, m = self.n, self.max_edges
+        ro, col, eid = np.zeros(n + 1, np.uint32), np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+        nid, ind, outd = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        e = self.lib.ref_pcsr_build(self.h, int(reverse), *[x.ctypes.data for x in (ro, col, eid, nid, ind, outd)])
+        return ro, col[:e].copy(), eid[:e].copy(), nid, ind, outd
+
+    def close(self):
+        if self.h:
+            self.lib.ref_pcsr_free(self.h)
+            self.h = None

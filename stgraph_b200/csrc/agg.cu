@@ -671,8 +671,10 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
     if constexpr (GROUP == 32 && MODE != kParts) {
       // measured on config 5 (F=100 / 128): 3.48 / 3.34 ms against 3.99 / 3.88 ms for one row per warp;
       // 4 resident blocks per SM beat 3 (4.2 ms) and 2 (5.2 ms), 5..8 with a shorter unroll do not help.
-      constexpr int kRowsPerWarp = 32;
       constexpr int MINB = 4;           // 8 / NACC neighbour rows in flight per lane keep this at <= 64 registers
+      // 32 rows per warp also on a 1/8 row slice of config 5 (306 K rows, two waves of blocks): 16 / 8 / 4 rows per
+      // warp measured 0.32 / 0.35 / 0.39 ms against 0.316 ms -- the queue's balancing beats finer block granularity.
+      constexpr int kRowsPerWarp = 32;
       constexpr int slots_per_block = (kBlockThreads / 32) * kRowsPerWarp;
       const int pblocks = (p.num_rows + slots_per_block - 1) / slots_per_block;
       if constexpr (VEC == 4 && NACC == 1) {

@@ -4,8 +4,10 @@ The reference keeps a Wheatman-Xu packed CSR on the HOST (``pcsr.cu:404-717``), 
 rebuilds a dense CSR into pinned memory per timestamp and copies it to the GPU
 (``pcsr.cu:748-883``).  Its compacted CSR lists every row back to front (descending neighbour id,
 ``pcsr.cu:842-855``) with 1-based labels; that view is reproduced bit for bit from the sorted key
-array by GPU kernels (``csrc/snapshot.cu``, ``descending_rows=1``).  "Parity unpinned" by reference
-outputs (the module needs a GPU runtime for its pinned buffers); pinned by ``oracle/structure.py``.
+array by GPU kernels (``csrc/snapshot.cu``, ``descending_rows=1``).  Pinned against the reference itself:
+``tests/golden/ref_pcsr.npz`` holds what the reference's ``pcsr.cu`` (compiled from where it lies,
+``oracle/build_ref.py``) builds at every timestamp of two streams, rolling forward and backward
+(``tests/test_gpu_golden.py::test_pcsr_graph_equals_reference_pcsr``).
 """
 from .dynamic_graph import KeyedDynamicGraph
 

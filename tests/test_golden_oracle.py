@@ -138,3 +138,50 @@ def test_reference_ir_matches_our_tracer(gk):
     k0, k1, _ = gk["gat_h8d16/kernels"]
     assert ops("gat_h8d16", k0) == ["Add", "Sub", "LeakyReLU", "exp", "AggSum"]
     assert ops("gat_h8d16", k1) == ["TrueDiv", "Mul", "AggSum"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PCSR: fixtures recorded from the reference's own host-side PCSR (pcsr.cu compiled from where it lies,
+# oracle/build_ref.py), driven like PCSRGraph drives it (pcsr_graph.py:45-166)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gp():
+    return np.load(os.path.join(GOLD, "ref_pcsr.npz"))
+
+
+def _snapshots(gp, tag):
+    flat, sizes = gp[f"{tag}/snap_edges"], gp[f"{tag}/snap_sizes"]
+    cuts = np.concatenate([[0], np.cumsum(sizes)])
+    return [[(int(a), int(b)) for a, b in flat[cuts[t]:cuts[t + 1]]] for t in range(len(sizes))]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_pcsr_oracle_equals_reference_pcsr(gp, tag):
+    """labelled_forward_view / labelled_backward_view (descending rows, 1-based labels) == what the reference's PMA
+    builds at every timestamp, rolling forward and rewinding; degrees too."""
+    n = int(gp[f"{tag}/num_nodes"])
+    snaps = _snapshots(gp, tag)
+    keys = S.snapshot_edge_sets(snaps)
+    for t, k in enumerate(keys):
+        f = S.labelled_forward_view(k, n, descending_rows=True)
+        b = S.labelled_backward_view(k, n, descending_rows=True)
+        for name in ("row_offset", "column_indices", "eids"):
+            np.testing.assert_array_equal(getattr(f, name), gp[f"{tag}/fwd/{t}/{name}"].astype(np.int32), err_msg=f"fwd {t} {name}")
+            np.testing.assert_array_equal(getattr(b, name), gp[f"{tag}/bwd/{t}/{name}"].astype(np.int32), err_msg=f"bwd {t} {name}")
+        # PCSRGraph.in_degrees() returns the reversed structure's out_degrees (pcsr_graph.py:108-114)
+        np.testing.assert_array_equal(f.row_degrees, gp[f"{tag}/fwd/{t}/pcsr_out_degrees"].astype(np.int32))
+        np.testing.assert_array_equal(f.col_degrees, gp[f"{tag}/fwd/{t}/pcsr_in_degrees"].astype(np.int32))
+        ids = gp[f"{tag}/fwd/{t}/node_ids"].astype(np.int64)          # tie order unspecified (std::sort)
+        assert sorted(ids.tolist()) == list(range(n)) and np.all(np.diff(f.row_degrees[ids]) <= 0)
+        if t < len(keys) - 1:                                           # the backward roll lands on the same snapshot
+            for name in ("row_offset", "column_indices", "eids"):
+                np.testing.assert_array_equal(getattr(b, name), gp[f"{tag}/rewind/{t}/{name}"].astype(np.int32),
+                                              err_msg=f"rewind {t} {name}")
+
+
+def test_pcsr_fixture_exercises_readd_and_mass_delete(gp):
+    snaps = _snapshots(gp, "a")
+    sets = [set(s) for s in snaps]
+    gone = (sets[0] - sets[1]) & sets[3]
+    assert gone, "an edge is deleted and re-added later"
+    assert min(len(s) for s in sets) <= 3 < max(len(s) for s in sets)

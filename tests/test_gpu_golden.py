@@ -150,3 +150,42 @@ def test_stock_gat_program_equals_reference_kernels(cuda, gs, gk, case, heads, d
                                                   gout.cpu(), return_mag=True)
     A.assert_close_rel(el.grad.cpu(), ref_del, rel=5e-5, abs_terms=m_el, what="d_el")
     A.assert_close_rel(er.grad.cpu(), ref_der, rel=5e-5, abs_terms=m_er, what="d_er")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PCSRGraph against the reference's own host-side PCSR (tests/golden/ref_pcsr.npz)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gp():
+    return np.load(os.path.join(GOLD, "ref_pcsr.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_pcsr_graph_equals_reference_pcsr(cuda, gp, tag):
+    """Forward roll over every timestamp, then the backward roll T-1 -> 0: row offsets, columns (descending rows),
+    1-based labels and degrees bit-identical to what pcsr.cu builds."""
+    from stgraph_b200.graph import PCSRGraph
+
+    n = int(gp[f"{tag}/num_nodes"])
+    flat, sizes = gp[f"{tag}/snap_edges"], gp[f"{tag}/snap_sizes"]
+    cuts = np.concatenate([[0], np.cumsum(sizes)])
+    snaps = [[(int(a), int(b)) for a, b in flat[cuts[t]:cuts[t + 1]]] for t in range(len(sizes))]
+    T = len(snaps)
+    G = PCSRGraph(snaps, n)
+    host = lambda t: t.cpu().numpy()
+
+    def same(csr, prefix):
+        for name in ("row_offset", "column_indices", "eids"):
+            np.testing.assert_array_equal(host(getattr(csr, name)), gp[f"{prefix}/{name}"].astype(np.int32),
+                                          err_msg=f"{prefix}/{name}")
+
+    for t in range(T):
+        G.get_graph(t)
+        same(G._forward_graph, f"{tag}/fwd/{t}")
+        np.testing.assert_array_equal(G.in_degrees(), gp[f"{tag}/fwd/{t}/pcsr_out_degrees"].astype(np.int32))
+        np.testing.assert_array_equal(G.out_degrees(), gp[f"{tag}/fwd/{t}/pcsr_in_degrees"].astype(np.int32))
+    for t in range(T - 1, -1, -1):
+        G.get_backward_graph(t)
+        same(G._backward_graph, f"{tag}/bwd/{t}")
+        if t < T - 1:
+            same(G._backward_graph, f"{tag}/rewind/{t}")
