@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   grid_dependency_wait();
 }
 
-template <int VEC, int GROUP, int NACC, int MODE>
+template <int VEC, int GROUP, int NACC, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams p) {
   using T = typename VecT<VEC>::type;
   constexpr int GROUPS_PER_WARP = 32 / GROUP;
@@ -512,9 +512,17 @@ __global__ void __launch_bounds__(kBlockThreads) agg_rows_kernel(const AggParams
   if (p.hub_threshold > 0 && (end - beg) > p.hub_threshold) return;  // hub kernel owns this row
 
   T acc[NACC];
+  if constexpr (PAIR) {        // same summation order as the row-queue kernel: a row's bits do not depend on the graph size
+    int c;
+    float m, s;
+    load_col<MODE>(p, beg, end, gl, c, m);
+    load_scale<MODE>(p, beg, end, gl, c, m, s);
+    accumulate_edges_pair<8, MODE>(p, beg, end, lane, acc[0], c, m, s);
+  } else {
 #pragma unroll
-  for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
-  accumulate_edges<VEC, GROUP, NACC, MODE>(p, beg, end, 0, 1, gl, gmask, acc);
+    for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
+    accumulate_edges<VEC, GROUP, NACC, MODE>(p, beg, end, 0, 1, gl, gmask, acc);
+  }
 
   const int orow = p.out_rows ? __ldg(p.out_rows + row) : row;
   const float r = p.rs ? __ldg(p.rs + orow) : 1.f;
@@ -668,7 +676,12 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
-    if constexpr (GROUP == 32 && MODE != kParts) {
+    // A small graph (fewer rows than two waves of warps) keeps one row per warp: the queue kernel would put 256 rows
+    // on each of a handful of SMs (Cora shape, F=100: 35 us against 7 us).
+    const bool queue = p.num_rows >= 2 * sm_count() * 4 * (kBlockThreads / 32);
+    bool launched = false;
+    if constexpr (GROUP == 32 && MODE != kParts) if (queue) {
+      launched = true;
       // measured on config 5 (F=100 / 128): 3.48 / 3.34 ms against 3.99 / 3.88 ms for one row per warp;
       // 4 resident blocks per SM beat 3 (4.2 ms) and 2 (5.2 ms), 5..8 with a shorter unroll do not help.
       constexpr int MINB = 4;           // 8 / NACC neighbour rows in flight per lane keep this at <= 64 registers
@@ -687,7 +700,14 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
       }
       STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC, MODE>, pblocks, kBlockThreads, stream,
                                  overlap, p, slots_per_block));
-    } else {
+    }
+    if constexpr (GROUP == 32 && VEC == 4 && NACC == 1 && MODE != kParts) {
+      if (!launched && p.width > 64 && pair_mode()) {
+        STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC, MODE, true>, blocks, kBlockThreads, stream, overlap, p));
+        launched = true;
+      }
+    }
+    if (!launched) {
       // narrow rows (several rows per warp): the lane groups of a warp diverge and the queue costs
       // more than it saves (F=64: 3.0 ms against 2.66 ms)
       STG_CUDA(launch_overlapped(agg_rows_kernel<VEC, GROUP, NACC, MODE>, blocks, kBlockThreads, stream, overlap, p));

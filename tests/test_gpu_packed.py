@@ -199,7 +199,7 @@ def test_packed_linearity_and_adjoint_large(cuda):
 
 
 @pytest.mark.parametrize("feat", [68, 72, 100, 124, 128])
-@pytest.mark.parametrize("n_e", [(700, 9000), (3000, 200000)])
+@pytest.mark.parametrize("n_e", [(700, 9000), (12000, 150000), (20000, 900000)])   # >= 9472 rows: row-queue kernel, pair form
 def test_pair_form_widths_and_row_lengths(cuda, feat, n_e):
     """The half-warp pair form of the edge loop (F = 68..128): odd/even row lengths, rows longer than one 32-edge
     batch, empty rows; plain and packed bit-identical, both within 1e-5 of the oracle."""
@@ -225,8 +225,8 @@ def test_pair_form_ignores_nonfinite_rows_it_does_not_sum(cuda):
     from stgraph_b200 import kernels
     from stgraph_b200.graph import StaticGraph
 
-    n, feat = 300, 100
-    src, dst = _graph(n, 4000, seed=77)
+    n, feat = 12000, 100                                 # >= 9472 rows: row-queue kernel, pair form
+    src, dst = _graph(n, 130000, seed=77)
     keep = src != 0
     src, dst = src[keep], dst[keep]                      # vertex 0 is nobody's in-neighbour
     g = StaticGraph(torch.from_numpy(np.stack([src, dst], 1)), None, n)
