@@ -162,6 +162,15 @@ int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host, int32_
                                 const float* row_scale_host, float* out_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/* The same without the final stream synchronisation: the H2D copies, the kernels and the D2H copy are only
+ * ENQUEUED on `stream`; out_host is valid once the caller has synchronised that stream.  Two calls on two
+ * streams with two scratch buffers overlap one call's H2D with the other's D2H (PCIe is full duplex), which
+ * halves the host-to-host time of a forward + backward step (bench.py `e2e`).  Host buffers must be pinned. */
+int stg_agg_scaled_sum_f32_host_async(const StgCsrView* g, const float* x_host, int32_t feat,
+                                const float* nbr_scale_host, const float* edge_scale_host,
+                                const float* row_scale_host, float* out_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
 /* Fused edge-softmax attention aggregation (one pass, online softmax per head):
  *   score_e = leaky_relu(el[col[e],h] + er[r,h]);  alpha = softmax over the row
  *   out[r,h,:] = sum_e alpha_e * feat[col[e],h,:]

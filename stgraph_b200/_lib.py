@@ -101,6 +101,8 @@ _SIGNATURES = {
                                          c_void_p], True),
     "stg_agg_scaled_sum_f32_host": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                                    c_void_p, c_void_p, c_size_t, c_void_p], True),
+    "stg_agg_scaled_sum_f32_host_async": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                                         c_void_p, c_void_p, c_size_t, c_void_p], True),
     "stg_gat_softmax_fwd_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                                c_float, c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_gat_softmax_bwd_f32": (ctypes.c_int, [_P(StgCsrView), _P(StgCsrView), c_void_p, c_void_p, c_void_p,

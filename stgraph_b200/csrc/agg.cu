@@ -843,10 +843,9 @@ STG_API int stg_agg_scaled_sum_f32(const StgCsrView* g, const float* x, int32_t 
   return agg_scaled_sum_device(g, x, feat, nbr_scale, edge_scale, row_scale, out, as_stream(stream));
 }
 
-STG_API int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host, int32_t feat,
-                                           const float* nbr_scale_host, const float* edge_scale_host,
-                                           const float* row_scale_host, float* out_host,
-                                           void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+static int agg_host_enqueue(const StgCsrView* g, const float* x_host, int32_t feat, const float* nbr_scale_host,
+                            const float* edge_scale_host, const float* row_scale_host, float* out_host,
+                            void* dev_scratch, size_t dev_scratch_bytes, void* stream, bool synchronize) {
   int rc = validate_view(g, edge_scale_host != nullptr);
   if (rc != STG_OK) return rc;
   STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
@@ -873,8 +872,24 @@ STG_API int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host
                              row_scale_host ? drs : nullptr, dout, s);
   if (rc != STG_OK) return rc;
   STG_CUDA(cudaMemcpyAsync(out_host, dout, n * feat * sizeof(float), cudaMemcpyDeviceToHost, s));
-  STG_CUDA(cudaStreamSynchronize(s));
+  if (synchronize) STG_CUDA(cudaStreamSynchronize(s));
   return STG_OK;
+}
+
+STG_API int stg_agg_scaled_sum_f32_host(const StgCsrView* g, const float* x_host, int32_t feat,
+                                        const float* nbr_scale_host, const float* edge_scale_host,
+                                        const float* row_scale_host, float* out_host,
+                                        void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  return agg_host_enqueue(g, x_host, feat, nbr_scale_host, edge_scale_host, row_scale_host, out_host, dev_scratch,
+                          dev_scratch_bytes, stream, true);
+}
+
+STG_API int stg_agg_scaled_sum_f32_host_async(const StgCsrView* g, const float* x_host, int32_t feat,
+                                              const float* nbr_scale_host, const float* edge_scale_host,
+                                              const float* row_scale_host, float* out_host,
+                                              void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  return agg_host_enqueue(g, x_host, feat, nbr_scale_host, edge_scale_host, row_scale_host, out_host, dev_scratch,
+                          dev_scratch_bytes, stream, false);
 }
 
 STG_API int stg_agg_scaled_sum_parts_f32(const StgCsrView* g, const float* const* x_parts, const int32_t* part_bounds,

@@ -176,15 +176,19 @@ def agg_scaled_sum_graph(csr, x: torch.Tensor, nbr_scale=None, edge_scale=None, 
 
 
 def agg_scaled_sum_host(view: _lib.StgCsrView, x_host: torch.Tensor, out_host: torch.Tensor, scratch: torch.Tensor,
-                        nbr_scale_host=None, edge_scale_host=None, row_scale_host=None):
-    """Host-buffer variant (H2D + kernel + D2H inside one C call); buffers should be pinned."""
+                        nbr_scale_host=None, edge_scale_host=None, row_scale_host=None, stream=None):
+    """Host-buffer variant (H2D + kernel + D2H inside one C call); buffers should be pinned.
+
+    ``stream`` (a ``torch.cuda.Stream``): enqueue only (``stg_agg_scaled_sum_f32_host_async``) -- ``out_host`` is valid
+    after ``stream.synchronize()``; calls on two streams with two scratch buffers overlap H2D with D2H."""
     global launch_count
     n = view.num_nodes
     feat = x_host.numel() // max(n, 1)
-    _lib.call("stg_agg_scaled_sum_f32_host", ctypes.byref(view), x_host.data_ptr(), feat,
+    fn = "stg_agg_scaled_sum_f32_host" if stream is None else "stg_agg_scaled_sum_f32_host_async"
+    _lib.call(fn, ctypes.byref(view), x_host.data_ptr(), feat,
               _lib.ptr(nbr_scale_host), _lib.ptr(edge_scale_host), _lib.ptr(row_scale_host),
               out_host.data_ptr(), scratch.data_ptr(), scratch.numel() * scratch.element_size(),
-              _lib.current_stream_ptr())
+              _lib.current_stream_ptr() if stream is None else stream.cuda_stream)
     launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
     return out_host
 
