@@ -253,6 +253,25 @@ typedef struct StgVmProgram {
 int stg_vm_run_f32(const StgCsrView* g, const StgVmProgram* prog, void* const* tensors, void* stream);
 
 /* --------------------------------------------------- graph structure ops */
+/* ------------------------------------------------- TGCN (GRU) cell, element-wise */
+/* The element-wise pieces of the TGCN cell (stgraph/nn/pytorch/temporal/tgcn.py:21-47) as three fused passes
+ * forward and three backward; the GEMMs between them stay cuBLAS.  All tensors are contiguous fp32 with n elements
+ * ([N, H] flattened) unless stated.
+ *   bias_clamp : a[r, c] = clamp(a[r, c] + bias[c], lo, hi) in place (bias may be NULL) -- GCNConv's bias add
+ *                (gcn_conv.py:184-186) and the cell's clamp(+-1e6) (tgcn.py:23) on the [N, 3H] aggregation output;
+ *   clamp_bwd  : d_a = d_y where lo < y < hi, else 0 (y = the clamped value);
+ *   reset      : hr = h * sigmoid(pr)                         (tgcn.py:33-41: R, then H * R for the candidate state)
+ *   update     : out = z * h + (1 - z) * tanh(ph), z = sigmoid(pz)                                  (tgcn.py:43-47)
+ * The backward entry points recompute the activations from the pre-activations. */
+int stg_bias_clamp_f32(float* a, const float* bias, int64_t rows, int32_t cols, float lo, float hi, void* stream);
+int stg_clamp_bwd_f32(const float* y, const float* d_y, float* d_a, int64_t n, float lo, float hi, void* stream);
+int stg_gru_reset_fwd_f32(const float* pr, const float* h, float* hr, int64_t n, void* stream);
+int stg_gru_reset_bwd_f32(const float* pr, const float* h, const float* d_hr, float* d_pr, float* d_h, int64_t n,
+                          void* stream);
+int stg_gru_update_fwd_f32(const float* pz, const float* ph, const float* h, float* out, int64_t n, void* stream);
+int stg_gru_update_bwd_f32(const float* pz, const float* ph, const float* h, const float* d_out, float* d_pz,
+                           float* d_ph, float* d_h, int64_t n, void* stream);
+
 /* Workspace needed by stg_csr_build for E edges / N nodes. */
 size_t stg_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes);
 

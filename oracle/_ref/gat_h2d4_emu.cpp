@@ -87,18 +87,18 @@ extern "C" void K8
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V63_tmp = 0;
-            int offset0 = dst_id * 2 + tx/4;int offset3 = dst_id * 8 + tx;
+            int offset1 = dst_id * 2 + tx/4;int offset3 = dst_id * 8 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset2 = src_id * 8 + tx;int offset1 = eid * 2 + tx/4;
+                int offset2 = src_id * 8 + tx;int offset0 = eid * 2 + tx/4;
                 
                 
                 
-                float V61_tmp = V59[offset1]/V60[offset0];
+                float V61_tmp = V59[offset0]/V60[offset1];
                 
                 
                 
@@ -150,11 +150,11 @@ extern "C" void K8
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = dst_id * 2 + tx/4;int offset2 = dst_id * 8 + tx;int offset1 = eid * 2 + tx/4;
+                int offset1 = dst_id * 2 + tx/4;int offset2 = dst_id * 8 + tx;int offset0 = eid * 2 + tx/4;
                 
                 
                 
-                float V61_tmp = V59[offset1]/V60[offset0];
+                float V61_tmp = V59[offset0]/V60[offset1];
                 
                 
                 
@@ -162,7 +162,7 @@ extern "C" void K8
                 
                 
                 
-                float V56_tmp = Velinb[offset3] + Vercen[offset0];
+                float V56_tmp = Velinb[offset3] + Vercen[offset1];
                 
                 
                 
@@ -174,7 +174,7 @@ extern "C" void K8
                 
                 
                 
-                float V70_tmp = 1/V60[offset0];
+                float V70_tmp = 1/V60[offset1];
                 
                 
                 
@@ -182,7 +182,7 @@ extern "C" void K8
                 
                 
                 
-                float V72_tmp = V64[offset2]/V60[offset0];
+                float V72_tmp = V64[offset2]/V60[offset1];
                 
                 
                 
@@ -198,7 +198,7 @@ extern "C" void K8
                 
                 
                 
-                float V79_tmp = V78_tmp*V59[offset1];
+                float V79_tmp = V78_tmp*V59[offset0];
                 
                 
                 
@@ -215,7 +215,7 @@ extern "C" void K8
                 
                 
                 V87_tmp = V81_tmp;
-                atomicAdd(V87+offset0, V87_tmp);
+                atomicAdd(V87+offset1, V87_tmp);
                 
                 V69_tmp += V68_tmp;
                 

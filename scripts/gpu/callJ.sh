@@ -1,0 +1,22 @@
+set -x
+mkdir -p gpurun_out
+timeout 300 python - <<'PY' > gpurun_out/refgat.log 2>&1
+import sys
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/scripts')
+import bench_reference_gpu as B
+B.run_gat()
+PY
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"vm_kernel" -s 20 -c 12 --csv --log-file gpurun_out/vm_launches.csv python scripts/prof_gat_stock.py > gpurun_out/vm_ncu.log 2>&1
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench2.log 2> gpurun_out/bench2.err
+cat gpurun_out/refgat.log | tail -5
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/vm_launches.csv')) if len(r)>10]
+h=rows[0]
+for r in rows[1:]:
+    d=dict(zip(h,r)); print(d['ID'], d['Kernel Name'][:50], d['Grid Size'], d['Block Size'], d['Metric Value'])
+PY
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench2.log').read())
+print(d['ms_per_step'], d['value'], d['e2e'])"

@@ -109,6 +109,13 @@ _SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_vm_run_f32": (ctypes.c_int, [_P(StgCsrView), _P(StgVmProgram), _P(c_void_p), c_void_p], True),
+    "stg_bias_clamp_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p], True),
+    "stg_clamp_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p], True),
+    "stg_gru_reset_fwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p], True),
+    "stg_gru_reset_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p], True),
+    "stg_gru_update_fwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p], True),
+    "stg_gru_update_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                              c_void_p], True),
     "stg_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int32], False),
     "stg_csr_build": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32] + [c_void_p] * 12
                       + [c_void_p, c_size_t, c_void_p], True),

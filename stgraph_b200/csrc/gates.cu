@@ -1,0 +1,155 @@
+// Fused element-wise pieces of the TGCN (GRU) cell for sm_100a.
+//
+// Reference: stgraph/nn/pytorch/temporal/tgcn.py:21-47 computes, per time step, on [N, H] tensors
+//     Z = sigmoid(linear_z([conv_z | H]))        R = sigmoid(linear_r([conv_r | H]))
+//     H~ = tanh(linear_h([conv_h | H * R]))      H' = Z * H + (1 - Z) * H~
+// with conv_* = clamp(GCNConv(X) , -1e6, 1e6) -- about sixteen separate element-wise kernels forward and thirty
+// backward, each a full pass over [N, H] (config 4: N = 10^6, H = 64).  The GEMMs stay cuBLAS; what is left is three
+// element-wise passes forward and three backward:
+//     bias_clamp:  a = clamp(a + bias, lo, hi)                    (in place on the aggregation output [N, 3H])
+//     reset:       hr = h * sigmoid(pr)
+//     update:      out = z * h + (1 - z) * tanh(ph),  z = sigmoid(pz)
+// Backward kernels recompute the activations from the saved pre-activations (no extra tensors are kept).
+// HBM-roofline kernels: algorithmic bytes = 4 * (tensors read + tensors written) * N * H.
+#include "common.cuh"
+
+namespace stg {
+namespace {
+
+constexpr int kGateThreads = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+inline int gate_blocks(int64_t n) {
+  const int64_t b = (n + kGateThreads - 1) / kGateThreads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+__global__ void __launch_bounds__(kGateThreads) bias_clamp_kernel(float* __restrict__ a, const float* __restrict__ bias,
+                                                                 int64_t n, int cols, float lo, float hi) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = a[i];
+    if (bias) v += __ldg(bias + static_cast<int>(i % cols));
+    a[i] = fminf(fmaxf(v, lo), hi);
+  }
+}
+
+// d_a = d_y where the clamped value lies strictly inside (lo, hi), else 0 (torch.clamp passes the gradient on the
+// closed interval of the UNCLAMPED value; the two differ only when the pre-clamp value equals a bound exactly)
+__global__ void __launch_bounds__(kGateThreads) clamp_bwd_kernel(const float* __restrict__ y, const float* __restrict__ d_y,
+                                                                float* __restrict__ d_a, int64_t n, float lo, float hi) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = y[i];
+    d_a[i] = (v > lo && v < hi) ? d_y[i] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kGateThreads) reset_fwd_kernel(const float* __restrict__ pr, const float* __restrict__ h,
+                                                                float* __restrict__ hr, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    hr[i] = h[i] * sigmoidf_(pr[i]);
+}
+
+__global__ void __launch_bounds__(kGateThreads) reset_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ h,
+                                                                const float* __restrict__ d_hr, float* __restrict__ d_pr,
+                                                                float* __restrict__ d_h, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float r = sigmoidf_(pr[i]);
+    const float g = d_hr[i];
+    d_pr[i] = g * h[i] * r * (1.f - r);
+    d_h[i] = g * r;
+  }
+}
+
+__global__ void __launch_bounds__(kGateThreads) update_fwd_kernel(const float* __restrict__ pz, const float* __restrict__ ph,
+                                                                 const float* __restrict__ h, float* __restrict__ out,
+                                                                 int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float z = sigmoidf_(pz[i]);
+    out[i] = z * h[i] + (1.f - z) * tanhf(ph[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kGateThreads) update_bwd_kernel(const float* __restrict__ pz, const float* __restrict__ ph,
+                                                                 const float* __restrict__ h, const float* __restrict__ d_out,
+                                                                 float* __restrict__ d_pz, float* __restrict__ d_ph,
+                                                                 float* __restrict__ d_h, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float z = sigmoidf_(pz[i]);
+    const float t = tanhf(ph[i]);
+    const float g = d_out[i];
+    d_pz[i] = g * (h[i] - t) * z * (1.f - z);
+    d_ph[i] = g * (1.f - z) * (1.f - t * t);
+    d_h[i] = g * z;
+  }
+}
+
+}  // namespace
+}  // namespace stg
+
+using namespace stg;
+
+STG_API int stg_bias_clamp_f32(float* a, const float* bias, int64_t rows, int32_t cols, float lo, float hi, void* stream) {
+  STG_CHECK_ARG(rows >= 0 && cols > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), cols);
+  STG_CHECK_ARG(lo <= hi, "clamp bounds out of order");
+  if (rows == 0) return STG_OK;
+  STG_CHECK_ARG(a != nullptr, "a is NULL");
+  const int64_t n = rows * cols;
+  bias_clamp_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(a, bias, n, cols, lo, hi);
+  STG_LAUNCH_CHECK("bias_clamp_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_clamp_bwd_f32(const float* y, const float* d_y, float* d_a, int64_t n, float lo, float hi, void* stream) {
+  STG_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return STG_OK;
+  STG_CHECK_ARG(y && d_y && d_a, "NULL tensor");
+  clamp_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(y, d_y, d_a, n, lo, hi);
+  STG_LAUNCH_CHECK("clamp_bwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_gru_reset_fwd_f32(const float* pr, const float* h, float* hr, int64_t n, void* stream) {
+  STG_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return STG_OK;
+  STG_CHECK_ARG(pr && h && hr, "NULL tensor");
+  reset_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(pr, h, hr, n);
+  STG_LAUNCH_CHECK("reset_fwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_gru_reset_bwd_f32(const float* pr, const float* h, const float* d_hr, float* d_pr, float* d_h, int64_t n,
+                                  void* stream) {
+  STG_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return STG_OK;
+  STG_CHECK_ARG(pr && h && d_hr && d_pr && d_h, "NULL tensor");
+  reset_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(pr, h, d_hr, d_pr, d_h, n);
+  STG_LAUNCH_CHECK("reset_bwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_gru_update_fwd_f32(const float* pz, const float* ph, const float* h, float* out, int64_t n, void* stream) {
+  STG_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return STG_OK;
+  STG_CHECK_ARG(pz && ph && h && out, "NULL tensor");
+  update_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(pz, ph, h, out, n);
+  STG_LAUNCH_CHECK("update_fwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_gru_update_bwd_f32(const float* pz, const float* ph, const float* h, const float* d_out, float* d_pz,
+                                   float* d_ph, float* d_h, int64_t n, void* stream) {
+  STG_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return STG_OK;
+  STG_CHECK_ARG(pz && ph && h && d_out && d_pz && d_ph && d_h, "NULL tensor");
+  update_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(pz, ph, h, d_out, d_pz, d_ph, d_h, n);
+  STG_LAUNCH_CHECK("update_bwd_kernel");
+  return STG_OK;
+}

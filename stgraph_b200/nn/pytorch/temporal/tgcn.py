@@ -7,9 +7,11 @@ clamped to +-1e6 exactly like the reference.
 ``fused=True`` keeps the parameters and the math but runs the three graph convolutions as ONE
 GEMM ``X @ [W_z | W_r | W_h]`` and ONE aggregation of width 3H through ``ops_gcn.gcn_aggregate``
 (every output column of a GEMM / of the aggregation is computed independently, so the values
-are the same as three separate convolutions up to cuBLAS tiling), with no tracing or executor work
-per step: the per-timestep cost is 2 kernel launches + the gate GEMMs, and a whole BPTT window can
-be captured in a CUDA graph.
+are the same as three separate convolutions up to cuBLAS tiling), the gates as GEMMs on column
+blocks (no concatenations) and the element-wise work as three fused passes (``ops_gru``: bias +
+clamp, reset gate, update gate + candidate state) instead of ~16 torch kernels, with no tracing or
+executor work per step; a whole BPTT window can be captured in a CUDA graph (SURVEY.md section
+8(f).1).
 """
 import torch
 
@@ -64,16 +66,22 @@ class TGCN(torch.nn.Module):
         norm = g.get_ndata("norm")
         if norm is None:
             raise KeyError("StaticGraph passed to GCNConv forward pass does not contain 'norm' node data")
+        from ....ops_gru import bias_clamp, gru_reset, gru_update
+
         hid = self.out_channels
         W = torch.cat((self.conv_z.weight, self.conv_r.weight, self.conv_h.weight), dim=1)
         b = torch.cat((self.conv_z.bias, self.conv_r.bias, self.conv_h.bias))
-        h = gcn_aggregate(g, torch.mm(X, W), norm, edge_weight) + b
-        h = torch.clamp(h, min=-1e6, max=1e6)
-        hz, hr, hh = h[:, :hid], h[:, hid:2 * hid], h[:, 2 * hid:]
-        Z = torch.sigmoid(self.linear_z(torch.cat((hz, H), dim=1)))
-        R = torch.sigmoid(self.linear_r(torch.cat((hr, H), dim=1)))
-        H_tilde = torch.tanh(self.linear_h(torch.cat((hh, H * R), dim=1)))
-        return Z * H + (1 - Z) * H_tilde
+        # bias add + clamp(+-1e6) in one in-place pass over the [N, 3H] aggregation output
+        h = bias_clamp(gcn_aggregate(g, torch.mm(X, W), norm, edge_weight), b, -1e6, 1e6)
+        hz, hr, hh = h.split(hid, dim=1)          # split: the backward is one concatenation, not three zero-filled slices
+
+        def gate(linear, a, c):      # linear(cat(a, c)) without materialising the concatenation: two GEMMs
+            return torch.addmm(torch.addmm(linear.bias, a, linear.weight[:, :hid].t()), c, linear.weight[:, hid:].t())
+
+        pz = gate(self.linear_z, hz, H)
+        pr = gate(self.linear_r, hr, H)
+        ph = gate(self.linear_h, hh, gru_reset(pr, H))          # H * sigmoid(pr)
+        return gru_update(pz, ph, H)                            # Z * H + (1 - Z) * tanh(ph)
 
     def forward(self, g, X, edge_weight=None, H=None):
         if self.fused:

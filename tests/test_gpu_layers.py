@@ -395,3 +395,59 @@ def test_stock_gat_vm_kernel_hub_rows(cuda):
     torch.autograd.backward([featg, elg, erg], [d_feat.double(), d_el.double(), d_er.double()])
     gx_ref = featg.grad.reshape(n, -1) @ layer.fc.weight.detach().cpu().double()
     A.assert_close_rel(x.grad.cpu(), gx_ref, rel=1e-4, abs_terms=sc(gx_ref), what="stock GAT dX (hub)")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused element-wise pieces of the TGCN cell (csrc/gates.cu, ops_gru.py) against plain torch
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (300, 16), (1000, 64), (4099, 48)])
+def test_gru_gate_ops_match_torch(cuda, shape):
+    from stgraph_b200.ops_gru import bias_clamp, gru_reset, gru_update
+
+    torch.manual_seed(sum(shape))
+    n, hdim = shape
+    mk = lambda scale=1.0: (scale * torch.randn(n, hdim, device=cuda)).requires_grad_()
+    # reset gate
+    pr, h = mk(3.0), mk()
+    ref = h * torch.sigmoid(pr)
+    got = gru_reset(pr, h)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    go = torch.randn_like(ref)
+    g_ref = torch.autograd.grad(ref, (pr, h), go)
+    g_got = torch.autograd.grad(got, (pr, h), go)
+    for a, b in zip(g_got, g_ref):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    # update gate + candidate state
+    pz, ph, h = mk(3.0), mk(2.0), mk()
+    z = torch.sigmoid(pz)
+    ref = z * h + (1 - z) * torch.tanh(ph)
+    got = gru_update(pz, ph, h)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    g_ref = torch.autograd.grad(ref, (pz, ph, h), go)
+    g_got = torch.autograd.grad(got, (pz, ph, h), go)
+    for a, b in zip(g_got, g_ref):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-6)
+    # bias + clamp, in place, with values on both sides of the bounds
+    a0 = (4.0 * torch.randn(n, hdim, device=cuda)).requires_grad_()
+    bias = torch.randn(hdim, device=cuda, requires_grad=True)
+    ref = torch.clamp(a0 + bias, min=-5.0, max=5.0)
+    got = bias_clamp(a0 * 1.0, bias, -5.0, 5.0)        # `* 1.0`: the op overwrites its (intermediate) input
+    assert torch.equal(got, ref)
+    g_ref = torch.autograd.grad(ref, (a0, bias), go)
+    g_got = torch.autograd.grad(got, (a0, bias), go)
+    torch.testing.assert_close(g_got[0], g_ref[0], rtol=0, atol=0)
+    torch.testing.assert_close(g_got[1], g_ref[1], rtol=1e-5, atol=1e-5)
+
+
+def test_gru_gate_ops_extreme_inputs(cuda):
+    """Saturated gates stay finite: sigmoid(+-100), tanh(+-50), and the +-1e6 clamp of the cell."""
+    from stgraph_b200.ops_gru import bias_clamp, gru_reset, gru_update
+
+    big = torch.tensor([[-100.0, -20.0, 0.0, 20.0, 100.0]], device=cuda)
+    h = torch.ones_like(big)
+    assert torch.allclose(gru_reset(big, h), torch.sigmoid(big), rtol=1e-5, atol=1e-30)
+    out = gru_update(big, 0.5 * big, h)
+    z = torch.sigmoid(big)
+    assert torch.isfinite(out).all() and torch.allclose(out, z * h + (1 - z) * torch.tanh(0.5 * big), rtol=1e-5, atol=1e-7)
+    a = torch.tensor([[-3e6, -1e6, 0.5, 1e6, 3e6]], device=cuda)
+    assert torch.equal(bias_clamp(a.clone(), None, -1e6, 1e6), torch.clamp(a, -1e6, 1e6))
