@@ -297,6 +297,10 @@ __device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
 // F=100 (profiles/r01_agg_ncu.md): the LSU data pipe is the busiest unit (77 % of peak), and the two
 // 32-lane broadcasts per edge are a third of its wavefronts; the halves' partial sums are merged once per
 // row with four SHFL.BFLY.  Fixed order: deterministic.  On return lane L holds the row's floats [4L, 4L+4).
+// Neighbour-row load of the pair form: a plain read-only load.  Measured alternatives on config 5 (4.84 ms/step):
+// L2 evict_last policy 4.80-4.85 ms (noise), no L1 allocation 6.24 ms (the 7 % of sectors that hit L1 matter).
+__device__ __forceinline__ float4 ldg_row(const float4* p) { return __ldg(p); }
+
 template <int UNROLL, int MODE>
 __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int beg, int end, int lane, float4& result,
                                                       int my_c, float my_m, float my_s) {
@@ -316,10 +320,10 @@ __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int be
     base1 = reinterpret_cast<const char*>(p.x + o1);
   }
   const bool live1 = (hl + 16) * 4 < p.width;   // chunk 0 is always inside the row (width > 64); F=100: 9 of 16 lanes
-  auto row0 = [&](int c) { return __ldg(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
+  auto row0 = [&](int c) { return ldg_row(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
   auto row1 = [&](int c) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live1) v = __ldg(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
+    if (live1) v = ldg_row(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
     return v;
   };
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
