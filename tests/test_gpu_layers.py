@@ -332,10 +332,17 @@ def test_fused_edge_softmax_hub_rows(cuda, heads, dim):
     extra = extra[extra != 0]
     src = np.concatenate([src, extra, np.zeros_like(extra)])       # vertex 0: hub destination AND hub source
     dst = np.concatenate([dst, np.zeros_like(extra), extra])
+    for v, deg in ((1, 300), (2, 700), (3, 129)):                  # medium hub rows: one CTA each (attention kernels)
+        other = np.arange(10, 10 + deg)
+        src = np.concatenate([src, other, np.full(deg, v)])
+        dst = np.concatenate([dst, np.full(deg, v), other])
     k = np.unique(src * n + dst)
     src, dst = (k // n).astype(np.int32), (k % n).astype(np.int32)
     g = StaticGraph(torch.from_numpy(np.stack([src, dst], 1)), None, n)
     assert int(g.in_degrees_tensor().max()) > csr_mod.HUB_THRESHOLD
+    from stgraph_b200 import ops_gat
+    deg_in = g.in_degrees_tensor()
+    assert int(((deg_in > ops_gat.GAT_HUB_THRESHOLD) & (deg_in <= 1024)).sum()) >= 3      # both hub tiers are exercised
     f = S.forward_csr(src, dst, n)
     tg = torch.Generator().manual_seed(3)
     el = (torch.randn(n, heads, 1, generator=tg) * 2).to(cuda).requires_grad_(True)
