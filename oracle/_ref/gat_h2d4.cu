@@ -22,18 +22,18 @@ extern "C" __global__ void K8
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V60_tmp = 0;
-            int offset1 = dst_id * 2 + tx;
+            int offset0 = dst_id * 2 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 2 + tx;int offset2 = eid * 2 + tx;
+                int offset1 = src_id * 2 + tx;int offset2 = eid * 2 + tx;
                 
                 
                 
-                float V56_tmp = Velinb[offset0] + Vercen[offset1];
+                float V56_tmp = Velinb[offset1] + Vercen[offset0];
                 
                 
                 
@@ -56,7 +56,7 @@ extern "C" __global__ void K8
             }
             
             
-            V60[offset1] = V60_tmp;
+            V60[offset0] = V60_tmp;
             
             
             

@@ -23,18 +23,18 @@ extern "C" void K4
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V22_tmp = 0;
-            int offset1 = dst_id * 8 + tx;
+            int offset0 = dst_id * 8 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 8 + tx;int offset2 = eid * 8 + tx;
+                int offset1 = src_id * 8 + tx;int offset2 = eid * 8 + tx;
                 
                 
                 
-                float V18_tmp = Velinb[offset0] + Vercen[offset1];
+                float V18_tmp = Velinb[offset1] + Vercen[offset0];
                 
                 
                 
@@ -57,7 +57,7 @@ extern "C" void K4
             }
             
             
-            V22[offset1] = V22_tmp;
+            V22[offset0] = V22_tmp;
             
             
             
@@ -87,18 +87,18 @@ extern "C" void K4
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V25_tmp = 0;
-            int offset1 = dst_id * 8 + tx/16;int offset3 = dst_id * 128 + tx;
+            int offset0 = dst_id * 8 + tx/16;int offset3 = dst_id * 128 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset2 = src_id * 128 + tx;int offset0 = eid * 8 + tx/16;
+                int offset2 = src_id * 128 + tx;int offset1 = eid * 8 + tx/16;
                 
                 
                 
-                float V23_tmp = V21[offset0]/V22[offset1];
+                float V23_tmp = V21[offset1]/V22[offset0];
                 
                 
                 
@@ -150,11 +150,11 @@ extern "C" void K4
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset1 = dst_id * 8 + tx/16;int offset2 = dst_id * 128 + tx;int offset0 = eid * 8 + tx/16;
+                int offset0 = dst_id * 8 + tx/16;int offset2 = dst_id * 128 + tx;int offset1 = eid * 8 + tx/16;
                 
                 
                 
-                float V23_tmp = V21[offset0]/V22[offset1];
+                float V23_tmp = V21[offset1]/V22[offset0];
                 
                 
                 
@@ -162,7 +162,7 @@ extern "C" void K4
                 
                 
                 
-                float V18_tmp = Velinb[offset3] + Vercen[offset1];
+                float V18_tmp = Velinb[offset3] + Vercen[offset0];
                 
                 
                 
@@ -174,7 +174,7 @@ extern "C" void K4
                 
                 
                 
-                float V32_tmp = 1/V22[offset1];
+                float V32_tmp = 1/V22[offset0];
                 
                 
                 
@@ -182,7 +182,7 @@ extern "C" void K4
                 
                 
                 
-                float V34_tmp = V26[offset2]/V22[offset1];
+                float V34_tmp = V26[offset2]/V22[offset0];
                 
                 
                 
@@ -198,7 +198,7 @@ extern "C" void K4
                 
                 
                 
-                float V41_tmp = V40_tmp*V21[offset0];
+                float V41_tmp = V40_tmp*V21[offset1];
                 
                 
                 
@@ -215,7 +215,7 @@ extern "C" void K4
                 
                 
                 V49_tmp = V43_tmp;
-                atomicAdd(V49+offset1, V49_tmp);
+                atomicAdd(V49+offset0, V49_tmp);
                 
                 V31_tmp += V30_tmp;
                 

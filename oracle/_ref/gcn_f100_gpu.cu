@@ -23,18 +23,18 @@ extern "C" __global__ void K12
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V95_tmp = 0;
-            int offset2 = dst_id * 100 + tx;int offset3 = dst_id * 1 + tx/100;
+            int offset2 = dst_id * 1 + tx/100;int offset3 = dst_id * 100 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 100 + tx;int offset1 = src_id * 1 + tx/100;
+                int offset0 = src_id * 1 + tx/100;int offset1 = src_id * 100 + tx;
                 
                 
                 
-                float V94_tmp = Vhinb[offset0]*Vnorminb[offset1];
+                float V94_tmp = Vhinb[offset1]*Vnorminb[offset0];
                 
                 
                 
@@ -50,8 +50,8 @@ extern "C" __global__ void K12
             
             
             
-            float V96_tmp = V95_tmp*Vnormcen[offset3];
-            V96[offset2] = V96_tmp;
+            float V96_tmp = V95_tmp*Vnormcen[offset2];
+            V96[offset3] = V96_tmp;
             
         }
     }
@@ -79,18 +79,18 @@ extern "C" __global__ void K12
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V100_tmp = 0;
-            int offset2 = src_id * 100 + tx;int offset3 = src_id * 1 + tx/100;
+            int offset2 = src_id * 1 + tx/100;int offset3 = src_id * 100 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = dst_id * 100 + tx;int offset1 = dst_id * 1 + tx/100;
+                int offset0 = dst_id * 1 + tx/100;int offset1 = dst_id * 100 + tx;
                 
                 
                 
-                float V98_tmp = V97[offset0]*Vnormcen[offset1];
+                float V98_tmp = V97[offset1]*Vnormcen[offset0];
                 
                 
                 
@@ -106,8 +106,8 @@ extern "C" __global__ void K12
             
             
             
-            float V101_tmp = V100_tmp*Vnorminb[offset3];
-            V101[offset2] = V101_tmp;
+            float V101_tmp = V100_tmp*Vnorminb[offset2];
+            V101[offset3] = V101_tmp;
             
         }
     }

@@ -23,18 +23,18 @@ extern "C" __global__ void K14
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V103_tmp = 0;
-            int offset2 = dst_id * 128 + tx;int offset3 = dst_id * 1 + tx/128;
+            int offset2 = dst_id * 1 + tx/128;int offset3 = dst_id * 128 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 128 + tx;int offset1 = src_id * 1 + tx/128;
+                int offset0 = src_id * 1 + tx/128;int offset1 = src_id * 128 + tx;
                 
                 
                 
-                float V102_tmp = Vhinb[offset0]*Vnorminb[offset1];
+                float V102_tmp = Vhinb[offset1]*Vnorminb[offset0];
                 
                 
                 
@@ -50,8 +50,8 @@ extern "C" __global__ void K14
             
             
             
-            float V104_tmp = V103_tmp*Vnormcen[offset3];
-            V104[offset2] = V104_tmp;
+            float V104_tmp = V103_tmp*Vnormcen[offset2];
+            V104[offset3] = V104_tmp;
             
         }
     }
@@ -79,7 +79,7 @@ extern "C" __global__ void K14
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V108_tmp = 0;
-            int offset2 = src_id * 128 + tx;int offset3 = src_id * 1 + tx/128;
+            int offset2 = src_id * 1 + tx/128;int offset3 = src_id * 128 + tx;
             
             for (int e=beg;e<end;++e) {
                 
@@ -106,8 +106,8 @@ extern "C" __global__ void K14
             
             
             
-            float V109_tmp = V108_tmp*Vnorminb[offset3];
-            V109[offset2] = V109_tmp;
+            float V109_tmp = V108_tmp*Vnorminb[offset2];
+            V109[offset3] = V109_tmp;
             
         }
     }

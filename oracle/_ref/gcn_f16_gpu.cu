@@ -23,18 +23,18 @@ extern "C" __global__ void K0
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V1_tmp = 0;
-            int offset2 = dst_id * 16 + tx;int offset3 = dst_id * 1 + tx/16;
+            int offset2 = dst_id * 1 + tx/16;int offset3 = dst_id * 16 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 16 + tx;int offset1 = src_id * 1 + tx/16;
+                int offset0 = src_id * 1 + tx/16;int offset1 = src_id * 16 + tx;
                 
                 
                 
-                float V0_tmp = Vhinb[offset0]*Vnorminb[offset1];
+                float V0_tmp = Vhinb[offset1]*Vnorminb[offset0];
                 
                 
                 
@@ -50,8 +50,8 @@ extern "C" __global__ void K0
             
             
             
-            float V2_tmp = V1_tmp*Vnormcen[offset3];
-            V2[offset2] = V2_tmp;
+            float V2_tmp = V1_tmp*Vnormcen[offset2];
+            V2[offset3] = V2_tmp;
             
         }
     }
@@ -79,18 +79,18 @@ extern "C" __global__ void K0
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V6_tmp = 0;
-            int offset2 = src_id * 16 + tx;int offset3 = src_id * 1 + tx/16;
+            int offset2 = src_id * 1 + tx/16;int offset3 = src_id * 16 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int dst_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = dst_id * 16 + tx;int offset1 = dst_id * 1 + tx/16;
+                int offset0 = dst_id * 1 + tx/16;int offset1 = dst_id * 16 + tx;
                 
                 
                 
-                float V4_tmp = V3[offset0]*Vnormcen[offset1];
+                float V4_tmp = V3[offset1]*Vnormcen[offset0];
                 
                 
                 
@@ -106,8 +106,8 @@ extern "C" __global__ void K0
             
             
             
-            float V7_tmp = V6_tmp*Vnorminb[offset3];
-            V7[offset2] = V7_tmp;
+            float V7_tmp = V6_tmp*Vnorminb[offset2];
+            V7[offset3] = V7_tmp;
             
         }
     }

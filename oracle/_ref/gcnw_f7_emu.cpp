@@ -23,18 +23,18 @@ extern "C" void K2
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V10_tmp = 0;
-            int offset3 = dst_id * 7 + tx;int offset4 = dst_id * 1 + tx/7;
+            int offset3 = dst_id * 1 + tx/7;int offset4 = dst_id * 7 + tx;
             
             for (int e=beg;e<end;++e) {
                 
                 int src_id = __ldg(column_indices + e);
                 int eid = __ldg(eids + e);
                 
-                int offset0 = src_id * 7 + tx;int offset1 = src_id * 1 + tx/7;int offset2 = eid * 1 + tx/7;
+                int offset0 = src_id * 1 + tx/7;int offset1 = src_id * 7 + tx;int offset2 = eid * 1 + tx/7;
                 
                 
                 
-                float V8_tmp = Vnorminb[offset1]*Vhinb[offset0];
+                float V8_tmp = Vnorminb[offset0]*Vhinb[offset1];
                 
                 
                 
@@ -54,8 +54,8 @@ extern "C" void K2
             
             
             
-            float V11_tmp = V10_tmp*Vnormcen[offset4];
-            V11[offset3] = V11_tmp;
+            float V11_tmp = V10_tmp*Vnormcen[offset3];
+            V11[offset4] = V11_tmp;
             
         }
     }
@@ -83,7 +83,7 @@ extern "C" void K2
         for (; tx<feat_len; tx+=blockDim.x) {
             
             float V16_tmp = 0;
-            int offset3 = src_id * 7 + tx;int offset4 = src_id * 1 + tx/7;
+            int offset3 = src_id * 1 + tx/7;int offset4 = src_id * 7 + tx;
             
             for (int e=beg;e<end;++e) {
                 
@@ -114,8 +114,8 @@ extern "C" void K2
             
             
             
-            float V17_tmp = V16_tmp*Vnorminb[offset4];
-            V17[offset3] = V17_tmp;
+            float V17_tmp = V16_tmp*Vnorminb[offset3];
+            V17[offset4] = V17_tmp;
             
         }
     }
