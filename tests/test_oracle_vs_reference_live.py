@@ -92,3 +92,58 @@ def test_pcsr_oracle_equals_reference_pcsr_on_random_streams(n, T, base, churn, 
             same(t - 1, False)
     finally:
         ref.close()
+
+
+HAVE_KERNELS = os.path.exists(os.path.join(RE.REF_DIR, "gcn_f16.so"))
+
+
+@pytest.mark.skipif(not (HAVE_CSR and HAVE_KERNELS), reason="oracle/_ref reference kernels not built")
+@pytest.mark.parametrize("case,feat,weighted", [("gcn_f16", 16, False), ("gcn_f100", 100, False), ("gcn_f128", 128, False),
+                                                ("gcnw_f7", 7, True)])
+@pytest.mark.parametrize("n,e,seed", [(12, 30, 0), (100, 1500, 1), (400, 6000, 2)])
+def test_aggregation_oracle_equals_reference_kernels_live(case, feat, weighted, n, e, seed):
+    """The CUDA kernels the reference's code generator emits for GCNConv (forward K0 on the in-edge CSR, backward K1 on
+    the out-edge CSR), executed on the CPU by the SIMT shim with the reference's own launch geometry, against
+    oracle/aggregate.py on random graphs (a star around vertex 0 makes one long row and many short ones)."""
+    import torch
+
+    from oracle import aggregate as A
+
+    src, dst = _graph(n, e, seed)
+    star = np.arange(1, n, dtype=np.int32)
+    k = np.unique(np.concatenate([src.astype(np.int64) * n + dst, star.astype(np.int64) * n, star.astype(np.int64)]))
+    src, dst = (k // n).astype(np.int32), (k % n).astype(np.int32)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    ne = src.shape[0]
+    rng = np.random.default_rng(seed + 7)
+    w = rng.uniform(0.1, 1.0, size=ne).astype(np.float32)
+    fwd, bwd = RE.reference_static_graph(src, dst, w, n)
+    kernels, lib = RE.load_case(case)
+    norm = rng.uniform(0.2, 1.0, size=(n, 1)).astype(np.float32)
+    h = rng.standard_normal((n, feat)).astype(np.float32)
+    gin = rng.standard_normal((n, feat)).astype(np.float32)
+    tensors = {"Vhinb": h, "Vnormcen": norm, "Vnorminb": norm}
+    if weighted:
+        tensors["Vedge_weight"] = w.reshape(ne, 1).copy()
+    grads = [gin]
+    outs = {}
+    for kern in kernels:
+        for name, vt, shp in zip(kern["args"], kern["arg_types"], kern["arg_shapes"]):
+            if name not in tensors:
+                lead = ne if vt == "EDGE" else n
+                tensors[name] = np.zeros([lead] + shp, np.float32) if name in kern["rets"] else grads.pop(0)
+        csr = fwd if kern["parallel_mode"] == "DstParallel" else bwd
+        RE.run_reference_kernel(lib, kern, tensors, csr, n)
+        outs[kern["direction"]] = torch.from_numpy(tensors[kern["rets"][0]])
+    f, b = S.forward_csr(src, dst, n), S.backward_csr(src, dst, n)
+    ht, gt, nt = torch.from_numpy(h), torch.from_numpy(gin), torch.from_numpy(norm).reshape(-1)
+    wt = torch.from_numpy(w) if weighted else None
+    cols = 4 if feat == 7 else feat          # trap T1: for F=7 the reference launches 4 lanes per node
+    mine_f, mine_b = A.gcn_forward(f, ht, nt, wt), A.gcn_backward(b, gt, nt, wt)
+    A.assert_close_rel(mine_f[:, :cols], outs["forward"][:, :cols], rel=3e-6,
+                       abs_terms=A.gcn_forward(f, ht.abs(), nt, wt)[:, :cols], what=f"{case} forward")
+    A.assert_close_rel(mine_b[:, :cols], outs["backward"][:, :cols], rel=3e-6,
+                       abs_terms=A.gcn_backward(b, gt.abs(), nt, wt)[:, :cols], what=f"{case} backward")
+    if feat == 7:
+        assert torch.count_nonzero(outs["forward"][:, 4:]) == 0      # the columns the reference never writes
