@@ -147,3 +147,49 @@ def test_aggregation_oracle_equals_reference_kernels_live(case, feat, weighted, 
                        abs_terms=A.gcn_backward(b, gt.abs(), nt, wt)[:, :cols], what=f"{case} backward")
     if feat == 7:
         assert torch.count_nonzero(outs["forward"][:, 4:]) == 0      # the columns the reference never writes
+
+
+@pytest.mark.skipif(not (HAVE_CSR and HAVE_KERNELS), reason="oracle/_ref reference kernels not built")
+@pytest.mark.parametrize("case,heads,dim", [("gat_h2d4", 2, 4), ("gat_h8d16", 8, 16)])
+@pytest.mark.parametrize("n,e,seed", [(30, 150, 0), (200, 2500, 1)])
+def test_stock_gat_oracle_equals_reference_kernels_live(case, heads, dim, n, e, seed):
+    """The three kernels the reference emits for GATConv as shipped (trap T2: a mean), forward and backward."""
+    import torch
+
+    from oracle import aggregate as A
+
+    src, dst = _graph(n, e, seed)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    ne = src.shape[0]
+    fwd, bwd = RE.reference_static_graph(src, dst, np.ones(ne, np.float32), n)
+    kernels, lib = RE.load_case(case)
+    rng = np.random.default_rng(seed + 11)
+    f32 = lambda *s: rng.standard_normal(s).astype(np.float32)
+    el, er, feat, gout = f32(n, heads, 1), f32(n, heads, 1), f32(n, heads, dim), f32(n, heads, dim)
+    tensors = {"Velinb": el, "Vercen": er, "Vfeat_srcinb": feat}
+    grads = [gout]
+    for kern in kernels:
+        for name, vt, shp in zip(kern["args"], kern["arg_types"], kern["arg_shapes"]):
+            if name not in tensors:
+                lead = ne if vt == "EDGE" else n
+                tensors[name] = np.zeros([lead] + shp, np.float32) if name in kern["rets"] else grads.pop(0)
+        RE.run_reference_kernel(lib, kern, tensors, fwd if kern["parallel_mode"] == "DstParallel" else bwd, n)
+    k0, k1, k2 = kernels
+    t = lambda name: torch.from_numpy(tensors[name])
+    f = S.forward_csr(src, dst, n)
+    out, o3, o4 = A.gat_stock_forward(f, t("Velinb"), t("Vercen"), t("Vfeat_srcinb"))
+    scale = lambda x: x.abs().mean() * torch.ones_like(x) + 1e-12
+    A.assert_close_rel(o3, t(k0["rets"][0]), rel=1e-6, abs_terms=scale(o3))
+    A.assert_close_rel(o4, t(k0["rets"][1]), rel=1e-6, abs_terms=scale(o4))
+    A.assert_close_rel(out, t(k1["rets"][0]), rel=3e-6, abs_terms=scale(out))
+    d_feat, d_el, d_er, m_feat, m_el, m_er = A.gat_stock_backward(f, t("Velinb"), t("Vercen"), t("Vfeat_srcinb"),
+                                                                  torch.from_numpy(gout), return_mag=True)
+    rets = [t(r) for r in k2["rets"]]
+    ref_dfeat = [r for r in rets if r.shape[-1] == dim and r.dim() == 3 and r.shape[1] == heads][0] if dim != 1 else rets[0]
+    small = [r for r in rets if r.shape[-1] == 1]
+    A.assert_close_rel(d_feat, ref_dfeat, rel=5e-6, abs_terms=scale(ref_dfeat), what="d_feat")
+    ref_der = min(small, key=lambda x: float(x.abs().max()))
+    ref_del = max(small, key=lambda x: float(x.abs().max()))
+    A.assert_close_rel(d_el, ref_del, rel=2e-5, abs_terms=m_el, what="d_el")
+    A.assert_close_rel(d_er, ref_der, rel=2e-5, abs_terms=m_er, what="d_er")
