@@ -495,6 +495,26 @@ def main():
                                             f"destination rows = {e_s} of {e_f} edges, F={FEAT}, best of 3; "
                                             f"throughput scaled by edge share", "seconds": t_cpu}
 
+    if rank == 0 and world == 1 and not args.no_extras and os.environ.get("STG_BENCH_EPOCHS", "1") != "0":
+        # ---- the other half of BASELINE.json's metric: GCN / TGCN epoch ms on configs 1 and 2 (scripts/bench_configs.py:
+        # the reference's training loops on the synthetic Cora- and WikiMaths-shaped inputs); secondary figures
+        try:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("stg_bench_configs", os.path.join(ROOT, "scripts", "bench_configs.py"))
+            bc = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bc)
+            bc.config1()
+            bc.config2()
+            c2 = bc.out.get("config2_tgcn_wikimaths_epoch_ms", {})
+            extras["epoch_ms"] = {
+                "config1_gcn_cora_2layer": bc.out.get("config1_gcn_cora_epoch_ms"),
+                "config2_tgcn_wikimaths_723_steps": {"drop_in_layers": c2.get("dropin"), "fused_cell": c2.get("fused"),
+                                                     "fused_cell_one_cuda_graph": c2.get("fused_cudagraph")},
+                "note": "fwd + bwd + Adam per epoch, synthetic data of the reference datasets' shapes (BASELINE.json configs 1-2)"}
+        except Exception as ex:      # secondary figures only
+            extras["epoch_ms"] = {"error": repr(ex)[:300]}
+
     if rank == 0:
         peak, peak_src = peaks()
         packed = world == 1 and bool(graph._forward_graph._meta_cache)
