@@ -498,17 +498,19 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras and os.environ.get("STG_BENCH_EPOCHS", "1") != "0":
         # ---- the other half of BASELINE.json's metric: GCN / TGCN epoch ms on configs 1 and 2 (scripts/bench_configs.py:
         # the reference's training loops on the synthetic Cora- and WikiMaths-shaped inputs); secondary figures
+        # (a separate process with a time limit: nothing that happens there can cost the main measurement)
         try:
-            import importlib.util
+            import tempfile
 
-            spec = importlib.util.spec_from_file_location("stg_bench_configs", os.path.join(ROOT, "scripts", "bench_configs.py"))
-            bc = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(bc)
-            bc.config1()
-            bc.config2()
-            c2 = bc.out.get("config2_tgcn_wikimaths_epoch_ms", {})
+            with tempfile.TemporaryDirectory() as tmp:
+                path = os.path.join(tmp, "configs.json")
+                env = dict(os.environ, STG_CONFIGS_OUT=path, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py"), "1", "2"], env=env, cwd=ROOT,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240, check=True)
+                res = json.load(open(path))
+            c2 = res.get("config2_tgcn_wikimaths_epoch_ms", {})
             extras["epoch_ms"] = {
-                "config1_gcn_cora_2layer": bc.out.get("config1_gcn_cora_epoch_ms"),
+                "config1_gcn_cora_2layer": res.get("config1_gcn_cora_epoch_ms"),
                 "config2_tgcn_wikimaths_723_steps": {"drop_in_layers": c2.get("dropin"), "fused_cell": c2.get("fused"),
                                                      "fused_cell_one_cuda_graph": c2.get("fused_cudagraph")},
                 "note": "fwd + bwd + Adam per epoch, synthetic data of the reference datasets' shapes (BASELINE.json configs 1-2)"}

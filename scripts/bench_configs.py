@@ -256,6 +256,7 @@ if __name__ == "__main__":
             traceback.print_exc()
             out[f"config{w}_error"] = repr(ex)[:400]
         torch.cuda.empty_cache()
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
+    path = os.environ.get("STG_CONFIGS_OUT", "gpurun_out/configs.json")
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out, indent=1))
