@@ -514,6 +514,9 @@ def main():
                 "config2_tgcn_wikimaths_723_steps": {"drop_in_layers": c2.get("dropin"), "fused_cell": c2.get("fused"),
                                                      "fused_cell_one_cuda_graph": c2.get("fused_cudagraph")},
                 "note": "fwd + bwd + Adam per epoch, synthetic data of the reference datasets' shapes (BASELINE.json configs 1-2)"}
+            for k_, v_ in res.items():
+                if k_.endswith("_error"):
+                    extras["epoch_ms"][k_] = str(v_)[:200]
         except Exception as ex:      # secondary figures only
             extras["epoch_ms"] = {"error": repr(ex)[:300]}
 
