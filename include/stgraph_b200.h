@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 1
+#define STG_ABI_VERSION 2
 
 typedef enum StgStatus {
   STG_OK = 0,
@@ -58,6 +58,12 @@ typedef struct StgCsrView {
   const int32_t* hub_count;
   int32_t hub_threshold;
   int32_t hub_capacity;
+  /* Optional global row queue of the aggregation kernels: two zero-initialised int32 counters in device
+   * memory owned by the graph object ({next chunk, finished blocks}).  The row kernel draws chunks of
+   * consecutive rows from it (so that all resident warps work inside one narrow window of rows and the
+   * source rows of a graph with locality stay in L2) and rearms it before it exits.  One queue per view
+   * and per stream: two launches that use the SAME queue must be ordered.  NULL = static block ranges. */
+  int32_t* work_queue;
 } StgCsrView;
 
 /* ------------------------------------------------------------------ misc */
@@ -129,6 +135,12 @@ int stg_agg_scaled_sum_rows_f32(const StgCsrView* g, const int32_t* out_rows, co
                                 const float* nbr_scale, const float* edge_scale, const float* row_scale, float* out,
                                 int32_t accumulate, void* stream);
 
+/* Row-subset form of the packed kernel: view row i is output row out_rows[i] (see stg_agg_scaled_sum_rows_f32);
+ * out_rows == NULL: identity.  The multi-GPU passes use it for both sub-CSRs of a rank (own-source edges over all
+ * rows, halo-source edges over the rows that have any). */
+int stg_agg_packed_sum_rows_f32(const StgCsrView* g, const StgEdgeMeta* meta, const int32_t* out_rows, const float* x,
+                                int32_t feat, const float* row_scale, float* out, int32_t accumulate, void* stream);
+
 /* Same operation with the source matrix ROW-PARTITIONED into num_parts blocks (multi-GPU): block q holds
  * rows [part_bounds[q], part_bounds[q+1]) of x and may live in a peer GPU's memory mapped into this
  * process (CUDA IPC / symmetric memory): the kernel then fetches remote neighbour rows with NVLink
@@ -152,6 +164,25 @@ int stg_halo_pull_f32(const float* const* x_parts, const int32_t* part_bounds, i
 int stg_halo_push_f32(const float* own, int32_t feat, const int64_t* send_rows, const int32_t* send_peer,
                       const int64_t* send_slot, int64_t n_items, float* const* peer_halo, int32_t num_parts,
                       int32_t max_blocks, void* stream);
+
+/* Copy-engine halo exchange (multi-GPU; new -- the reference is single-GPU).
+ *   stg_rows_gather_f32 : buf[j,:] = own[rows[j],:], j < n  -- packs the rows the peers need, grouped by peer;
+ *   stg_halo_send_f32   : one cudaMemcpyAsync per peer q != my_rank of rows [send_off[q], send_off[q+1]) of
+ *                         send_buf to peer_dst[q] (an address inside peer q's halo buffer, mapped into this
+ *                         process: CUDA IPC / symmetric memory).  send_off / peer_dst are HOST arrays;
+ *   stg_peer_signal     : after everything enqueued so far on `stream`, write `value` to *peer_flags[q] for every
+ *                         q != my_rank (release, system scope);
+ *   stg_peer_wait       : block `stream` (a one-warp spinning kernel) until flags[q] >= value for every
+ *                         q != my_rank (acquire, system scope); gives up after timeout_cycles SM clocks
+ *                         (<= 0: 2^32) and then sets *status = 1 + q (status may be NULL).
+ * No SM takes part in the transfer itself, so it overlaps the own-source aggregation pass for free. */
+int stg_rows_gather_f32(const float* own, int32_t feat, const int64_t* rows, int64_t n, float* buf, int32_t max_blocks,
+                        void* stream);
+int stg_halo_send_f32(const float* send_buf, int32_t feat, int32_t num_parts, int32_t my_rank, const int64_t* send_off,
+                      float* const* peer_dst, void* stream);
+int stg_peer_signal(int32_t* const* peer_flags, int32_t num_parts, int32_t my_rank, int32_t value, void* stream);
+int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, int64_t timeout_cycles,
+                  int32_t* status, void* stream);
 
 /* Same operation with HOST buffers: copies x (and the scale vectors) to the
  * device scratch the caller provides, runs the kernel, copies out back.

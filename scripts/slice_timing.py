@@ -17,6 +17,8 @@ x = torch.randn(n, F, device=dev)
 csr = g._forward_graph
 bounds = edge_balanced_bounds(csr.row_offset, P)
 keep = []
+import os
+USE_QUEUE = os.environ.get('STG_SLICE_QUEUE', '1') != '0'
 
 def mkview(ro, cols, n_rows):
     cap = int(cols.shape[0]) // HUB_THRESHOLD + 1
@@ -29,6 +31,8 @@ def mkview(ro, cols, n_rows):
     v.num_nodes, v.num_edges, v.eid_base, v.eids_identity = n_rows, int(cols.shape[0]), 0, 1
     v.hub_rows = hr.data_ptr() if has else None; v.hub_count = hc.data_ptr() if has else None
     v.hub_threshold = HUB_THRESHOLD if has else 0; v.hub_capacity = cap if has else 0
+    if USE_QUEUE:
+        q = torch.zeros(2, dtype=torch.int32, device=dev); keep.append(q); v.work_queue = q.data_ptr()
     return v
 
 def timeit(fn, reps=20):

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STG_B200_LIB") or os.path.join(_HERE, "lib", "libstgraph_b200.so")   # env: A/B builds only
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2
 VM_MAX_TENSORS = 24
 VM_MAX_INSTR = 96
 VM_MAX_REGS = 48
@@ -38,6 +39,7 @@ class StgCsrView(Structure):
         ("hub_count", c_void_p),
         ("hub_threshold", c_int32),
         ("hub_capacity", c_int32),
+        ("work_queue", c_void_p),
     ]
 
 
@@ -95,6 +97,12 @@ _SIGNATURES = {
                                                       c_void_p, c_int32, c_int32, c_void_p], True),
     "stg_halo_push_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, _P(c_void_p), c_int32,
                                          c_int32, c_void_p], True),
+    "stg_agg_packed_sum_rows_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                                   c_void_p, c_int32, c_void_p], True),
+    "stg_rows_gather_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p], True),
+    "stg_halo_send_f32": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, _P(c_int64), _P(c_void_p), c_void_p], True),
+    "stg_peer_signal": (ctypes.c_int, [_P(c_void_p), c_int32, c_int32, c_int32, c_void_p], True),
+    "stg_peer_wait": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,
                                                     c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_halo_pull_f32": (ctypes.c_int, [_P(c_void_p), _P(c_int32), c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32,
@@ -165,7 +173,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.stg_abi_version() != 1:
+    if lib.stg_abi_version() != ABI_VERSION:
         raise RuntimeError("libstgraph_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

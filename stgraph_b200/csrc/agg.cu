@@ -53,6 +53,8 @@ struct AggParams {
   const int32_t* __restrict__ hub_count;
   const int32_t* __restrict__ out_rows;   // view row -> output row (NULL: identity)
   const int2* __restrict__ meta;          // PACKED mode: {column, scale bits} of every CSR slot (stg_csr_pack_edge_meta_f32)
+  int far_window;                         // > 0: sources further than this from the row are fetched with an L2 evict_first hint
+  int* queue;                             // global row queue {next chunk, finished blocks} (StgCsrView::work_queue) or NULL
   int num_rows;
   int num_edges;
   int eid_base;
@@ -301,9 +303,21 @@ __device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
 // L2 evict_last policy 4.80-4.85 ms (noise), no L1 allocation 6.24 ms (the 7 % of sectors that hit L1 matter).
 __device__ __forceinline__ float4 ldg_row(const float4* p) { return __ldg(p); }
 
-template <int UNROLL, int MODE>
+// L2 eviction hints (HINT): on a graph with community structure most sources of a row lie in a window of ids around
+// it and are re-read from L2 by the neighbouring rows, while the far ("random") 10 % of the edges stream 2.5 GB of
+// rows through L2 that nobody reads again.  Far sources are fetched evict_first, near ones evict_last, selected
+// per edge without a branch (the policy is a 64-bit register operand of ld.global.L2::cache_hint).
+__device__ __forceinline__ float4 ldg_row_hint(const float4* p, unsigned long long policy) {
+  float4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "l"(policy));
+  return v;
+}
+
+template <int UNROLL, int MODE, bool HINT = false>
 __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int beg, int end, int lane, float4& result,
-                                                      int my_c, float my_m, float my_s) {
+                                                      int my_c, float my_m, float my_s, int row = 0) {
   static_assert(UNROLL % 2 == 0, "two edges per step");
   constexpr int STEPS = UNROLL / 2;
   const int half = lane >> 4;
@@ -320,10 +334,25 @@ __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int be
     base1 = reinterpret_cast<const char*>(p.x + o1);
   }
   const bool live1 = (hl + 16) * 4 < p.width;   // chunk 0 is always inside the row (width > 64); F=100: 9 of 16 lanes
-  auto row0 = [&](int c) { return ldg_row(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
+  unsigned long long pol_far = 0, pol_near = 0;
+  if constexpr (HINT) {
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_far));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_near));
+  }
+  auto policy = [&](int c) { return (abs(c - row) > p.far_window) ? pol_far : pol_near; };
+  auto row0 = [&](int c) {
+    const float4* a = reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes);
+    if constexpr (HINT) return ldg_row_hint(a, policy(c));
+    else return ldg_row(a);
+  };
   auto row1 = [&](int c) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live1) v = ldg_row(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
+    const float4* a = reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes);
+    if constexpr (HINT) {
+      if (live1) v = ldg_row_hint(a, policy(c));
+    } else {
+      if (live1) v = ldg_row(a);
+    }
     return v;
   };
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
@@ -419,7 +448,14 @@ __device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, b
 // (row_offset -> column index -> neighbour scale -> neighbour rows) is spread over four consecutive
 // loop iterations: while row i is being summed, the scales of row i+1, the columns of row i+2 and
 // the offsets of row i+3 are already in flight.
-template <int VEC, int GROUP, int NACC, int MINB, int UNROLL, int MODE, bool PAIR = false>
+//
+// GQ (global queue) form: a persistent grid (resident blocks only) whose WARPS draw chunks of `slots_per_block`
+// consecutive slots from ONE device-wide counter (StgCsrView::work_queue), the next chunk id being fetched while
+// the current chunk is summed.  All resident warps then work inside one narrow, moving window of destination
+// rows (4736 warps x 8 rows = 38 K rows, 15 MB of x on config 5, against the 151 K-row window of 592 resident
+// 256-row blocks), so the source rows of a community graph are re-read from L2, not from HBM, and no block
+// waits for its longest row at the tail.  The last block to finish resets the counters for the next launch.
+template <int VEC, int GROUP, int NACC, int MINB, int UNROLL, int MODE, bool PAIR = false, bool GQ = false, bool HINT = false>
 __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(const AggParams p, int slots_per_block) {
   using T = typename VecT<VEC>::type;
   constexpr int GPW = 32 / GROUP;
@@ -429,15 +465,40 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   const int gidx = lane / GROUP;
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(GROUP - 1)));
   const int total_slots = (p.num_rows + GPW - 1) / GPW;
-  const int first = blockIdx.x * slots_per_block;
-  const int last = min(first + slots_per_block, total_slots);
-  if (threadIdx.x == 0) next_slot = first;
-  __syncthreads();
+  const int first = GQ ? 0 : blockIdx.x * slots_per_block;
+  const int last = GQ ? total_slots : min(first + slots_per_block, total_slots);
+  int q_cur = 0, q_pos = slots_per_block, q_nxt = 0;   // GQ: chunk being walked, position in it, chunk id in flight
+  if constexpr (GQ) {
+    if (lane == 0) q_nxt = atomicAdd(p.queue, 1);
+  } else {
+    if (threadIdx.x == 0) next_slot = first;
+    __syncthreads();
+  }
 
   auto draw = [&]() {
-    int s = 0;
-    if (lane == 0) s = atomicAdd(&next_slot, 1);
-    return __shfl_sync(0xffffffffu, s, 0);
+    if constexpr (GQ) {
+      if (q_pos == slots_per_block && q_cur < total_slots) {      // warp-uniform
+        q_cur = __shfl_sync(0xffffffffu, q_nxt, 0) * slots_per_block;
+        q_pos = 0;
+        if (lane == 0 && q_cur < total_slots) q_nxt = atomicAdd(p.queue, 1);
+      }
+      return q_cur + q_pos++;
+    } else {
+      int s = 0;
+      if (lane == 0) s = atomicAdd(&next_slot, 1);
+      return __shfl_sync(0xffffffffu, s, 0);
+    }
+  };
+  auto finish = [&]() {
+    if constexpr (GQ) {          // the last block to get here has seen every chunk drawn: rearm the queue
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(p.queue + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        p.queue[0] = 0;
+        p.queue[1] = 0;
+        __threadfence();
+      }
+    }
+    grid_dependency_wait();
   };
   // stage A: slot -> output row, [beg, end); end = -1 when there is nothing to do (past the end, hub row)
   auto stage_a = [&](int slot, int& row, int& beg, int& end) {
@@ -456,7 +517,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
   int row2, beg2, end2;                // offsets in flight
   float s0, r0, m0, m1;                // m*: scale that arrived WITH the column (kPacked)
   slot0 = draw();
-  if (slot0 >= last) return;
+  if (slot0 >= last) { finish(); return; }
   stage_a(slot0, row0, beg0, end0);
   int slot1 = draw();
   stage_a(slot1, row1, beg1, end1);
@@ -486,7 +547,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
       T acc[NACC];
       if constexpr (PAIR) {
         static_assert(VEC == 4 && GROUP == 32 && NACC == 1, "pair form: one row per warp, float4 lanes");
-        accumulate_edges_pair<UNROLL, MODE>(p, beg0, end0, lane, acc[0], c0, 0.f, s0);
+        accumulate_edges_pair<UNROLL, MODE, HINT>(p, beg0, end0, lane, acc[0], c0, 0.f, s0, slot0);
       } else {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
@@ -498,7 +559,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
     slot1 = slot2; row1 = row2; beg1 = beg2; end1 = end2; c1 = c2; m1 = m2;
     slot2 = slot3; row2 = row3; beg2 = beg3; end2 = end3;
   }
-  grid_dependency_wait();
+  finish();
 }
 
 template <int VEC, int GROUP, int NACC, int MODE, bool PAIR = false>
@@ -665,6 +726,25 @@ inline bool pair_mode() {
   return on;
 }
 
+// Slots a warp draws from the global row queue at a time (STG_AGG_CHUNK; 0 = static block ranges; read once).
+inline int queue_chunk() {
+  static const int v = [] {
+    const char* e = getenv("STG_AGG_CHUNK");
+    const int c = e ? atoi(e) : 4;
+    return c < 0 ? 0 : (c > 4096 ? 4096 : c);
+  }();
+  return v;
+}
+
+// Sources further than this many ids from their row get the L2 evict_first hint (STG_AGG_FAR; 0 = no hints; read once).
+inline int far_window() {
+  static const int v = [] {
+    const char* e = getenv("STG_AGG_FAR");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 template <int VEC, int GROUP, int NACC, int MODE>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
@@ -694,16 +774,32 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
       constexpr int kRowsPerWarp = 32;
       constexpr int slots_per_block = (kBlockThreads / 32) * kRowsPerWarp;
       const int pblocks = (p.num_rows + slots_per_block - 1) / slots_per_block;
+      // global row queue (the view carries its counters): resident blocks only, warps draw chunks of queue_chunk() slots
+      const bool gq = p.queue != nullptr && queue_chunk() > 0;
+      const int gblocks = std::min(sm_count() * MINB, (p.num_rows + 7) / 8);
       if constexpr (VEC == 4 && NACC == 1) {
         if (p.width > 64 && pair_mode()) {
-          STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true>, pblocks, kBlockThreads,
-                                     stream, overlap, p, slots_per_block));
+          if (gq && p.far_window > 0 && MODE != kParts) {
+            STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true, true, true>, gblocks,
+                                       kBlockThreads, stream, overlap, p, queue_chunk()));
+          } else if (gq) {
+            STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true, true>, gblocks, kBlockThreads,
+                                       stream, overlap, p, queue_chunk()));
+          } else {
+            STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true>, pblocks, kBlockThreads,
+                                       stream, overlap, p, slots_per_block));
+          }
           STG_LAUNCH_CHECK("agg_rows_pipe_kernel (pair)");
           return STG_OK;
         }
       }
-      STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC, MODE>, pblocks, kBlockThreads, stream,
-                                 overlap, p, slots_per_block));
+      if (gq) {
+        STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC, MODE, false, true>, gblocks,
+                                   kBlockThreads, stream, overlap, p, queue_chunk()));
+      } else {
+        STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8 / NACC, MODE>, pblocks, kBlockThreads, stream,
+                                   overlap, p, slots_per_block));
+      }
     }
     if constexpr (GROUP == 32 && VEC == 4 && NACC == 1 && MODE != kParts) {
       if (!launched && p.width > 64 && pair_mode()) {
@@ -762,6 +858,8 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   AggParams p;
   p.out_rows = out_rows;
   p.meta = reinterpret_cast<const int2*>(meta);
+  p.queue = g->work_queue;
+  p.far_window = far_window();
   p.accumulate = accumulate;
   p.nparts = nparts;
   for (int q = 0; q < STG_MAX_PARTS; ++q) p.xs[q] = q < nparts ? parts[q] : nullptr;
@@ -993,4 +1091,20 @@ STG_API int stg_agg_packed_sum_strided_f32(const StgCsrView* g, const StgEdgeMet
 STG_API int stg_agg_packed_sum_f32(const StgCsrView* g, const StgEdgeMeta* meta, const float* x, int32_t feat,
                                    const float* row_scale, float* out, int32_t accumulate, void* stream) {
   return stg_agg_packed_sum_strided_f32(g, meta, x, feat, feat, row_scale, out, feat, accumulate, stream);
+}
+
+STG_API int stg_agg_packed_sum_rows_f32(const StgCsrView* g, const StgEdgeMeta* meta, const int32_t* out_rows,
+                                        const float* x, int32_t feat, const float* row_scale, float* out,
+                                        int32_t accumulate, void* stream) {
+  int rc = validate_view(g, false);
+  if (rc != STG_OK) return rc;
+  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
+  STG_CHECK_ARG(accumulate >= 0 && accumulate <= 2, "accumulate must be 0, 1 or 2 (got %d)", accumulate);
+  if (g->num_nodes == 0) return STG_OK;
+  STG_CHECK_ARG(g->num_edges == 0 || (meta != nullptr && aligned8(meta)),
+                "meta must be a non-NULL, 8-byte aligned device pointer");
+  STG_CHECK_ARG(x != nullptr && out != nullptr, "x / out is NULL");
+  STG_CHECK_ARG(x != out, "x and out must not alias");
+  return agg_scaled_sum_device(g, x, feat, nullptr, nullptr, row_scale, out, as_stream(stream), 0, nullptr, nullptr,
+                               accumulate, out_rows, g->num_edges == 0 ? nullptr : meta);
 }

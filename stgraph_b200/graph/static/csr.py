@@ -175,6 +175,9 @@ class CSR:
                 v.hub_count = None
                 v.hub_threshold = 0
                 v.hub_capacity = 0
+            # global row queue of the aggregation kernel (StgCsrView::work_queue): owned by this direction of the graph
+            self._work_queue = torch.zeros(2, dtype=torch.int32, device=self.row_offset.device)
+            v.work_queue = self._work_queue.data_ptr()
             self._view = v
         return self._view
 

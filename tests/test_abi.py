@@ -32,13 +32,13 @@ def test_python_binding_covers_header():
 
 def test_load_and_version():
     lib = _lib.load()
-    assert lib.stg_abi_version() == 1
+    assert lib.stg_abi_version() == _lib.ABI_VERSION
     assert lib.stg_last_error() is not None
 
 
 def test_struct_layouts_match_header():
     # sizes implied by the C declarations (LP64)
-    assert ctypes.sizeof(_lib.StgCsrView) == 4 * 8 + 4 * 4 + 2 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.StgCsrView) == 4 * 8 + 4 * 4 + 2 * 8 + 2 * 4 + 8   # + work_queue (ABI 2)
     assert ctypes.sizeof(_lib.StgVmInstr) == 16
     assert ctypes.sizeof(_lib.StgVmTensor) == 16
     assert ctypes.sizeof(_lib.StgVmProgram) == 8 * 4 + 8 * _lib.VM_MAX_ACC + 16 * _lib.VM_MAX_TENSORS + 16 * _lib.VM_MAX_INSTR
