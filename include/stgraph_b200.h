@@ -172,14 +172,22 @@ int stg_halo_push_f32(const float* own, int32_t feat, const int64_t* send_rows, 
  *                         process: CUDA IPC / symmetric memory).  send_off / peer_dst are HOST arrays;
  *   stg_peer_signal     : after everything enqueued so far on `stream`, write `value` to *peer_flags[q] for every
  *                         q != my_rank (release, system scope);
- *   stg_peer_wait       : block `stream` (a one-warp spinning kernel) until flags[q] >= value for every
- *                         q != my_rank (acquire, system scope); gives up after timeout_cycles SM clocks
+ *   stg_peer_wait       : block `stream` (a one-warp spinning kernel) until flags[q] has reached value (compared
+ *                         modulo 2^16: ((flags[q] - value) & 0xFFFF) < 0x8000) for every q != my_rank
+ *                         (acquire, system scope); gives up after timeout_cycles SM clocks
  *                         (<= 0: 2^32) and then sets *status = 1 + q (status may be NULL).
  * No SM takes part in the transfer itself, so it overlaps the own-source aggregation pass for free. */
 int stg_rows_gather_f32(const float* own, int32_t feat, const int64_t* rows, int64_t n, float* buf, int32_t max_blocks,
                         void* stream);
 int stg_halo_send_f32(const float* send_buf, int32_t feat, int32_t num_parts, int32_t my_rank, const int64_t* send_off,
                       float* const* peer_dst, void* stream);
+/* The three steps above in one call, with the flags written by the copy engines as well: gather, P-1 data copies,
+ * then for every peer q one 4-byte copy seq_values[value] -> *peer_flags[q] (seq_values: device table with
+ * seq_values[j] == j for j < 65536; value: this step's sequence number modulo 2^16, which is how stg_peer_wait
+ * compares).  Nothing after the gather needs an SM. */
+int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t* send_rows, const int64_t* send_off,
+                          float* send_buf, float* const* peer_dst, int32_t* const* peer_flags, const int32_t* seq_values,
+                          int32_t value, int32_t num_parts, int32_t my_rank, int32_t gather_blocks, void* stream);
 int stg_peer_signal(int32_t* const* peer_flags, int32_t num_parts, int32_t my_rank, int32_t value, void* stream);
 int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, int64_t timeout_cycles,
                   int32_t* status, void* stream);
@@ -282,6 +290,17 @@ typedef struct StgVmProgram {
 /* Runs the program once per (row, lane) of the given view (rows = "center" side). Tensors written
  * with a reducing STORE must be zero-filled by the caller (atomic accumulation may be used). */
 int stg_vm_run_f32(const StgCsrView* g, const StgVmProgram* prog, void* const* tensors, void* stream);
+
+/* ------------------------------------------------ link-prediction decode */
+/* out[p] = sum_f z[a[p], f] * z[b[p], f] for p < n_pairs (a, b: int64 vertex ids, z: [N, feat] fp32).
+ * Replaces STGraphTGCN.decode of the dynamic-temporal benchmark
+ * (benchmarking/dynamic-temporal-tgcn/seastar/model.py:18-21: two [P, F] gathers, a multiply, a row sum). */
+int stg_edge_dot_f32(const float* z, int32_t feat, const int64_t* a, const int64_t* b, int64_t n_pairs, float* out,
+                     void* stream);
+/* Its backward: d_z[a[p], :] += grad_out[p] * z[b[p], :] and d_z[b[p], :] += grad_out[p] * z[a[p], :]
+ * (vector red.global.add; d_z must be zero-filled or hold the gradient to add to). */
+int stg_edge_dot_bwd_f32(const float* z, int32_t feat, const int64_t* a, const int64_t* b, int64_t n_pairs,
+                         const float* grad_out, float* d_z, void* stream);
 
 /* --------------------------------------------------- graph structure ops */
 /* ------------------------------------------------- TGCN (GRU) cell, element-wise */

@@ -89,8 +89,67 @@ def make_pcsr_golden():
     print("wrote", os.path.join(GOLD, "ref_pcsr.npz"), len(out), "arrays")
 
 
+def reference_graph_updates(snaps, n):
+    """``graph_updates`` exactly as the reference computes them: its own ``DynamicGraph._preprocess_graph_structure``
+    (``/root/reference/stgraph/graph/dynamic/dynamic_graph.py:56-79``, pure Python) is loaded from where it lies and run
+    on the snapshot lists; only its base-class import is stubbed (the ABC pulls in the CUDA-backed graph modules)."""
+    import importlib.util
+    import types
+
+    saved = {k: sys.modules.get(k) for k in ("stgraph", "stgraph.graph", "stgraph.graph.stgraph_base")}
+    base = types.ModuleType("stgraph.graph.stgraph_base")
+
+    class STGraphBase:              # stand-in for the abstract base (no behaviour on this path)
+        def __init__(self):
+            pass
+
+    base.STGraphBase = STGraphBase
+    sys.modules["stgraph"] = types.ModuleType("stgraph")
+    sys.modules["stgraph.graph"] = types.ModuleType("stgraph.graph")
+    sys.modules["stgraph.graph.stgraph_base"] = base
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "_ref_dynamic_graph", "/root/reference/stgraph/graph/dynamic/dynamic_graph.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+
+        class Concrete(mod.DynamicGraph):
+            def _get_cached_graph(self, timestamp):
+                return False
+
+            def __getattr__(self, name):        # the remaining abstract hooks are never reached here
+                raise AttributeError(name)
+
+        Concrete.__abstractmethods__ = frozenset()
+        g = Concrete([[tuple(map(int, e)) for e in s] for s in snaps], n)
+        return g.graph_updates
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def make_updates_golden():
+    """a9: per-timestamp add / delete lists of three update streams, computed by the reference's own preprocessing."""
+    out = {}
+    for tag, (n, T, base, churn, seed) in {"a": (60, 7, 300, 40, 3), "b": (24, 6, 70, 25, 11), "c": (500, 8, 4000, 700, 29)}.items():
+        snaps = dynamic_stream(n, T, base, churn, seed)
+        ups = reference_graph_updates(snaps, n)
+        out[f"{tag}/num_nodes"] = np.int32(n)
+        out[f"{tag}/snap_edges"] = np.array([e for s in snaps for e in s], dtype=np.int32).reshape(-1, 2)
+        out[f"{tag}/snap_sizes"] = np.array([len(s) for s in snaps], dtype=np.int32)
+        for t in range(T):
+            for kind in ("add", "delete"):
+                out[f"{tag}/{t}/{kind}"] = np.array(ups[str(t)][kind], dtype=np.int32).reshape(-1, 2)
+    np.savez_compressed(os.path.join(GOLD, "ref_updates.npz"), **out)
+    print("wrote", os.path.join(GOLD, "ref_updates.npz"), len(out), "arrays")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    make_updates_golden()
     n, e = 40, 200
     src, dst = make_graph(n, e, 0)
     rng = np.random.default_rng(1)

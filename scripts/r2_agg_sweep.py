@@ -52,7 +52,7 @@ def no_queue(view):
     return v
 
 
-for F in (100, 47, 128, 64):
+for F in [int(v) for v in os.environ.get("STG_SWEEP_F", "100,47,128,64").split(",")]:
     x = torch.randn(n, F, device=dev)
     out = torch.empty_like(x)
     out2 = torch.empty_like(x)

@@ -101,6 +101,8 @@ _SIGNATURES = {
                                                    c_void_p, c_int32, c_void_p], True),
     "stg_rows_gather_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p], True),
     "stg_halo_send_f32": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, _P(c_int64), _P(c_void_p), c_void_p], True),
+    "stg_halo_exchange_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, _P(c_int64), c_void_p, _P(c_void_p), _P(c_void_p),
+                                              c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p], True),
     "stg_peer_signal": (ctypes.c_int, [_P(c_void_p), c_int32, c_int32, c_int32, c_void_p], True),
     "stg_peer_wait": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,
@@ -117,6 +119,8 @@ _SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_vm_run_f32": (ctypes.c_int, [_P(StgCsrView), _P(StgVmProgram), _P(c_void_p), c_void_p], True),
+    "stg_edge_dot_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p], True),
+    "stg_edge_dot_bwd_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], True),
     "stg_bias_clamp_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p], True),
     "stg_clamp_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p], True),
     "stg_gru_reset_fwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p], True),

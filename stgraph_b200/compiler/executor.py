@@ -198,8 +198,12 @@ class Executor:
         for unit in mu:
             self._alloc_unit_outputs(unit, self.ts.current_tensor_map)
         kernel_arg_list = [[v.id for v in u.kernel_args()] for u in mu]
-        ret_tensors = FuncWrapper.apply(self, uid, kernel_arg_list, rets,
-                                        *[self.ts.current_tensor_map[v.id] for v in inputs])
+        in_tensors = [self.ts.current_tensor_map[v.id] for v in inputs]
+        # The state stacks are popped by backward_cb only: push when a backward can follow (the reference pushes on
+        # every call, executor.py:377-380, so inference / validation loops grow its stacks without bound).
+        self._will_backward = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
+                                                              for t in in_tensors)
+        ret_tensors = FuncWrapper.apply(self, uid, kernel_arg_list, rets, *in_tensors)
         # only tensors returned by the Function carry grad_fn: re-track them (executor.py:343-346)
         for var, t in zip(rets, ret_tensors):
             self.ts.track_tensor(var.id, t)
@@ -236,9 +240,10 @@ class Executor:
         for unit in mu:
             for la in unit.launches:
                 self.run_launch(la, tm, self.graph)
-        self.ts.tensor_map_stack.push({k: tm[k] for k in self.saved_for_backward if k in tm})
-        if _is_dynamic(self.graph):
-            self.ts.graph_timestamp_stack.push(self.graph.current_timestamp)
+        if getattr(self, "_will_backward", True):
+            self.ts.tensor_map_stack.push({k: tm[k] for k in self.saved_for_backward if k in tm})
+            if _is_dynamic(self.graph):
+                self.ts.graph_timestamp_stack.push(self.graph.current_timestamp)
         return tuple(tm[r.id] for r in rets)
 
     # -- backward ---------------------------------------------------------------------

@@ -423,7 +423,8 @@ __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int be
 // Scaled row result -> out (assign / += / red.add).
 template <int VEC, int GROUP, int NACC>
 __device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, bool nonempty, float r,
-                                          typename VecT<VEC>::type (&acc)[NACC]) {
+                                          typename VecT<VEC>::type (&acc)[NACC], bool have_old,
+                                          typename VecT<VEC>::type (&old)[NACC]) {
   using T = typename VecT<VEC>::type;
   float* dst = p.out + static_cast<size_t>(row) * p.ld_out;
 #pragma unroll
@@ -435,9 +436,33 @@ __device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, b
         if (nonempty) red_add(dst + o, acc[k]);
         continue;
       }
-      if (p.accumulate) add_vec(acc[k], *reinterpret_cast<const T*>(dst + o));
+      if (p.accumulate) add_vec(acc[k], have_old ? old[k] : *reinterpret_cast<const T*>(dst + o));
       st_row<VEC>(dst + o, acc[k]);
     }
+  }
+}
+
+template <int VEC, int GROUP, int NACC>
+__device__ __forceinline__ void write_row(const AggParams& p, int row, int gl, bool nonempty, float r,
+                                          typename VecT<VEC>::type (&acc)[NACC]) {
+  typename VecT<VEC>::type none[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) zero_vec(none[k]);
+  write_row<VEC, GROUP, NACC>(p, row, gl, nonempty, r, acc, false, none);
+}
+
+// accumulate == 1 (out += ...): the row's current value, requested BEFORE its edges are walked so that the read
+// overlaps the gathers (the halo-source pass of the multi-GPU path: ~2.5 edges per row, where a second dependent
+// DRAM round trip per row doubled the pass).
+template <int VEC, int GROUP, int NACC>
+__device__ __forceinline__ void prefetch_row(const AggParams& p, int row, int gl, typename VecT<VEC>::type (&old)[NACC]) {
+  using T = typename VecT<VEC>::type;
+  const float* dst = p.out + static_cast<size_t>(row) * p.ld_out;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    const int o = (gl + k * GROUP) * VEC;
+    zero_vec(old[k]);
+    if (o < p.width) old[k] = *reinterpret_cast<const T*>(dst + o);
   }
 }
 
@@ -545,6 +570,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
 
     if (end0 >= 0) {
       T acc[NACC];
+      T old[NACC];
+      const bool rmw = NACC <= 2 && p.accumulate == 1;       // wider tiles have no registers to spare for it
+      if constexpr (NACC <= 2) {
+        if (rmw) prefetch_row<VEC, GROUP, NACC>(p, row0, gl, old);
+      }
       if constexpr (PAIR) {
         static_assert(VEC == 4 && GROUP == 32 && NACC == 1, "pair form: one row per warp, float4 lanes");
         accumulate_edges_pair<UNROLL, MODE, HINT>(p, beg0, end0, lane, acc[0], c0, 0.f, s0, slot0);
@@ -553,7 +583,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
         for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
         accumulate_edges<VEC, GROUP, NACC, UNROLL, MODE>(p, beg0, end0, 0, 1, gl, gmask, acc, c0, s0);
       }
-      write_row<VEC, GROUP, NACC>(p, row0, gl, end0 > beg0, r0, acc);
+      write_row<VEC, GROUP, NACC>(p, row0, gl, end0 > beg0, r0, acc, rmw, old);
     }
     slot0 = slot1; row0 = row1; beg0 = beg1; end0 = end1; c0 = c1; s0 = s1; r0 = r1;
     slot1 = slot2; row1 = row2; beg1 = beg2; end1 = end2; c1 = c2; m1 = m2;

@@ -153,7 +153,7 @@ __global__ void peer_wait_kernel(const int32_t* flags, int nparts, int rank, int
     int v;
     for (;;) {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
-      if (v - value >= 0) break;
+      if (((v - value) & 0xFFFF) < 0x8000) break;        // sequence numbers live modulo 2^16 (stg_halo_exchange_f32)
       if (clock64() - t0 > timeout_cycles) {
         if (status) atomicExch(status, 1 + q);
         break;
@@ -275,5 +275,29 @@ STG_API int stg_halo_pull_f32(const float* const* x_parts, const int32_t* part_b
   if (feat % 4 == 0 && al16) halo_pull_kernel<4><<<blocks, kPullThreads, 0, as_stream(stream)>>>(p);
   else halo_pull_kernel<1><<<blocks, kPullThreads, 0, as_stream(stream)>>>(p);
   STG_LAUNCH_CHECK("halo_pull_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t* send_rows, const int64_t* send_off,
+                                  float* send_buf, float* const* peer_dst, int32_t* const* peer_flags,
+                                  const int32_t* seq_values, int32_t value, int32_t num_parts, int32_t my_rank,
+                                  int32_t gather_blocks, void* stream) {
+  STG_CHECK_ARG(num_parts >= 1 && num_parts <= STG_MAX_PARTS, "num_parts must be in [1, %d]", STG_MAX_PARTS);
+  STG_CHECK_ARG(my_rank >= 0 && my_rank < num_parts && feat > 0, "bad rank / feat");
+  STG_CHECK_ARG(send_off && peer_dst && peer_flags && seq_values, "NULL argument");
+  STG_CHECK_ARG(value >= 0 && value < 65536, "sequence value must be in [0, 65536)");
+  const int64_t n_send = send_off[num_parts];
+  int rc = stg_rows_gather_f32(own, feat, send_rows, n_send, send_buf, gather_blocks, stream);
+  if (rc != STG_OK) return rc;
+  rc = stg_halo_send_f32(send_buf, feat, num_parts, my_rank, send_off, peer_dst, stream);
+  if (rc != STG_OK) return rc;
+  // arrival flags by the copy engines too: 4 bytes of a device-resident table of sequence numbers, stream-ordered
+  // behind the data copies -- a signalling KERNEL would have to wait for a free SM slot behind the persistent
+  // aggregation grid (measured: 0.47 ms for a one-warp kernel).
+  for (int i = 1; i < num_parts; ++i) {
+    const int q = (my_rank + i) % num_parts;
+    if (peer_flags[q] == nullptr) continue;
+    STG_CUDA(cudaMemcpyAsync(peer_flags[q], seq_values + value, sizeof(int32_t), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  }
   return STG_OK;
 }

@@ -109,6 +109,9 @@ class HaloPlan:
         v.hub_count = hub_count.data_ptr() if has_hubs else None
         v.hub_threshold = HUB_THRESHOLD if has_hubs else 0
         v.hub_capacity = cap if has_hubs else 0
+        queue = torch.zeros(2, dtype=torch.int32, device=dev)      # global row queue of the aggregation kernel
+        self._keep.append(queue)
+        v.work_queue = queue.data_ptr()
         return v
 
     def split_views(self):

@@ -64,34 +64,163 @@ class _LocalSlice:
         self.num_local_edges = e_local
 
 
+def cost_balanced_bounds(fwd_row_offset: torch.Tensor, bwd_row_offset: torch.Tensor, world: int, row_cost: int = 4) -> list[int]:
+    """ONE set of vertex boundaries for both directions: every range holds ~1/P of ``in_deg + out_deg + 2*row_cost``.
+
+    A vertex is a row of the forward CSR (cost ~ in-degree) and of the backward CSR (cost ~ out-degree); a row also
+    has a fixed cost (offsets, scale, output row: ``row_cost`` edge-equivalents, measured ~4 at F=100), so ranges
+    of many short rows are not under-estimated.  One partition means one owner per feature row AND per gradient
+    row, which is what a layer stack needs (the output rows of a layer are the source rows of the next).
+    """
+    n = int(fwd_row_offset.shape[0] - 1)
+    cost = (fwd_row_offset[1:] - fwd_row_offset[:-1]).to(torch.int64) + (bwd_row_offset[1:] - bwd_row_offset[:-1]).to(torch.int64)
+    cost = cost + 2 * int(row_cost)
+    pre = torch.zeros(n + 1, dtype=torch.int64, device=cost.device)
+    pre[1:] = torch.cumsum(cost, 0)
+    total = int(pre[-1].item())
+    targets = torch.arange(1, world, dtype=torch.int64, device=cost.device) * total // max(world, 1)
+    cuts = torch.searchsorted(pre, targets, right=False).clamp_(0, n)
+    b = [0] + [int(c) for c in cuts.cpu()] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
 class PartitionedGraph:
-    """A StaticGraph replicated on every rank, with this rank's row slices of both directions."""
+    """A StaticGraph row-partitioned over ``world`` GPUs (structure replicated, rows of every node tensor sharded).
 
-    def __init__(self, graph, rank: int, world: int):
+    Rank r owns the vertices ``[bounds[r], bounds[r+1])``: their feature rows, their output rows (forward, in-edge
+    CSR) and their gradient rows (backward, out-edge CSR).  ``GCNConv.forward(pg, h_local)`` takes and returns the
+    local rows only; :meth:`aggregate` is the distributed form of ``stg_agg_scaled_sum_f32``.
+    """
+
+    def __init__(self, graph, rank: int, world: int, group=None, bounds=None, row_cost: int = 4):
         self.graph = graph
-        self.rank, self.world = rank, world
-        self.fwd_bounds = edge_balanced_bounds(graph._forward_graph.row_offset, world)
-        self.bwd_bounds = edge_balanced_bounds(graph._backward_graph.row_offset, world)
-        self.fwd = _LocalSlice(graph._forward_graph, self.fwd_bounds[rank], self.fwd_bounds[rank + 1])
-        self.bwd = _LocalSlice(graph._backward_graph, self.bwd_bounds[rank], self.bwd_bounds[rank + 1])
+        self.rank, self.world, self.group = rank, world, group
+        f, b = graph._forward_graph, graph._backward_graph
+        self.bounds = list(bounds) if bounds is not None else cost_balanced_bounds(f.row_offset, b.row_offset, world, row_cost)
+        self.fwd_bounds = self.bwd_bounds = self.bounds
+        self.own_lo, self.own_hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_own = self.own_hi - self.own_lo
+        self.fwd = _LocalSlice(f, self.own_lo, self.own_hi)
+        self.bwd = _LocalSlice(b, self.own_lo, self.own_hi)
+        self._plans = None
+        self._exchanges = {}
+        self._halo_scalars = {}
+        self._ndata = {}
 
+    # ---- graph-object surface the layers use (stgraph_base.py:51-59 names) ------------------------------
+    def get_num_nodes(self) -> int:
+        return self.graph.get_num_nodes()
+
+    def get_num_edges(self) -> int:
+        return self.graph.get_num_edges()
+
+    def num_local_nodes(self) -> int:
+        return self.n_own
+
+    def local(self, t: torch.Tensor) -> torch.Tensor:
+        """My rows of a replicated ``[N, ...]`` tensor."""
+        return t[self.own_lo:self.own_hi]
+
+    def set_ndata(self, name: str, value: torch.Tensor):
+        """Node data of MY vertices (``[n_own, ...]``)."""
+        if value.shape[0] != self.n_own:
+            raise ValueError(f"ndata '{name}' must have {self.n_own} rows (the local vertices), got {value.shape[0]}")
+        self._ndata[name] = value
+
+    def get_ndata(self, name: str):
+        return self._ndata.get(name)
+
+    def degree_norm(self) -> torch.Tensor:
+        """``in_degree^-0.5`` of my vertices, ``[n_own, 1]`` (``benchmarking/gcn/seastar/train.py:53-57``)."""
+        return self.local(self.graph.degree_norm()).contiguous()
+
+    # ---- exchange plans / engines ---------------------------------------------------------------------------
     def halo_plans(self, group=None):
-        """Halo-only exchange plans: (forward, backward).
-
-        Feature rows are owned by the forward (destination) partition -- layer outputs are produced
-        there -- and gradient rows likewise; the backward aggregation computes the source rows of
-        ``bwd_bounds`` and fetches the gradient rows it needs from their forward owners.
-        """
+        """Halo-only exchange plans: (forward, backward); built once (collective: every rank must call it)."""
         from .halo import HaloPlan
 
-        g = self.graph
-        fwd = HaloPlan(g._forward_graph, self.fwd_bounds, self.fwd_bounds, self.rank, self.world, group)
-        bwd = HaloPlan(g._backward_graph, self.bwd_bounds, self.fwd_bounds, self.rank, self.world, group)
-        return fwd, bwd
+        if self._plans is None:
+            g = self.graph
+            grp = group if group is not None else self.group
+            self._plans = (HaloPlan(g._forward_graph, self.bounds, self.bounds, self.rank, self.world, grp),
+                           HaloPlan(g._backward_graph, self.bounds, self.bounds, self.rank, self.world, grp))
+        return self._plans
+
+    def halo_scalars(self, direction: str, own_values: torch.Tensor) -> torch.Tensor:
+        """Per-vertex scalars (e.g. ``norm``) of the halo vertices of one direction: one exchange, then cached."""
+        key = (direction, own_values.data_ptr(), own_values._version)
+        if key not in self._halo_scalars:
+            plan = self.halo_plans()[0 if direction == "fwd" else 1]
+            self._halo_scalars = {k: v for k, v in self._halo_scalars.items() if k[0] != direction}
+            self._halo_scalars[key] = (plan.halo_vector(own_values.reshape(-1).contiguous()), own_values)
+        return self._halo_scalars[key][0]
+
+    def exchange(self, direction: str, feat: int, nbr_scale: torch.Tensor | None):
+        """The :class:`HaloExchange` of (direction, width, source scale); collective on first use."""
+        from .exchange import HaloExchange
+
+        key = (direction, int(feat), None if nbr_scale is None else (nbr_scale.data_ptr(), nbr_scale._version))
+        ex = self._exchanges.get(key)
+        if ex is None:
+            plan = self.halo_plans()[0 if direction == "fwd" else 1]
+            ns_own = None if nbr_scale is None else nbr_scale.reshape(-1).contiguous()
+            ns_halo = None if nbr_scale is None else self.halo_scalars(direction, ns_own)
+            ex = HaloExchange(plan, feat, ns_own, ns_halo)
+            ex._scale_ref = nbr_scale
+            self._exchanges[key] = ex
+        return ex
+
+    def aggregate(self, direction: str, x_own: torch.Tensor, nbr_scale=None, row_scale=None, out=None) -> torch.Tensor:
+        """``out[v] = row_scale[v] * sum_{u in nbrs(v)} nbr_scale[u] * x[u]`` for my vertices ``v``; every tensor holds
+        local rows only (``[n_own, ...]``), remote source rows travel as halo (see ``dist/exchange.py``)."""
+        if x_own.shape[0] != self.n_own:
+            raise ValueError(f"x_own must hold the {self.n_own} local rows, got {x_own.shape[0]}")
+        x_own = x_own.contiguous()
+        feat = x_own.numel() // max(self.n_own, 1)
+        if out is None:
+            out = torch.empty_like(x_own)
+        rs = None if row_scale is None else row_scale.reshape(-1).contiguous()
+        return self.exchange(direction, feat, nbr_scale).aggregate(x_own.reshape(self.n_own, feat), rs, out)
 
     def local_rows(self, direction: str):
-        b = self.fwd_bounds if direction == "fwd" else self.bwd_bounds
-        return b[self.rank], b[self.rank + 1]
+        return self.own_lo, self.own_hi
+
+
+class _PartitionedGcnAggregate(torch.autograd.Function):
+    """Autograd bridge of the distributed GCN aggregation: forward on the in-edge CSR, backward on the out-edge CSR
+    (a gather both ways, like the reference's K0/K1 pair, ``gcn_conv.py:162-166``)."""
+
+    @staticmethod
+    def forward(ctx, pg, h, norm):
+        ctx.pg, ctx.norm = pg, norm
+        return pg.aggregate("fwd", h, norm, norm)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, ctx.pg.aggregate("bwd", grad_out.contiguous(), ctx.norm, ctx.norm), None
+
+
+def partitioned_gcn_aggregate(pg: PartitionedGraph, h: torch.Tensor, norm: torch.Tensor) -> torch.Tensor:
+    return _PartitionedGcnAggregate.apply(pg, h, norm)
+
+
+def all_reduce_gradients(module_or_params, group=None):
+    """Sum the (replicated) parameters' gradients over the ranks: each rank back-propagates through its own rows only
+    ("dense weights are replicated; their gradients need one tiny all-reduce")."""
+    import torch.distributed as dist
+
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
 
 
 def exchange_rows(full: torch.Tensor, bounds: list[int], group=None):

@@ -32,6 +32,8 @@ def keys_of(edges, reverse: bool, num_nodes: int, dev) -> torch.Tensor:
     e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
     if e.shape[0] == 0:
         return torch.empty(0, dtype=torch.int64, device=dev)
+    if int(e.min()) < 0 or int(e.max()) >= int(num_nodes):       # host array: free to check (see csr._edges_to_device)
+        raise ValueError(f"vertex ids must lie in [0, {int(num_nodes)}): found ids in [{int(e.min())}, {int(e.max())}]")
     src = torch.from_numpy(e[:, 0].copy()).to(device=dev, dtype=torch.int32)      # .copy(): fresh, positively strided
     dst = torch.from_numpy(e[:, 1].copy()).to(device=dev, dtype=torch.int32)
     # keys_from_edges packs (dst << 32) | src, i.e. rows = second endpoint

@@ -130,7 +130,7 @@ class DynamicGraph(STGraphBase):
         prev = torch.empty(0, dtype=torch.int64, device=self.device)
         self._base_keys = None
         for t in range(len(edge_list)):
-            src, dst = _edges_to_device(edge_list[t], self.device)
+            src, dst = _edges_to_device(edge_list[t], self.device, self.max_num_nodes)
             cur = keys_from_edges(src, dst, self.max_num_nodes)
             if t == 0:
                 add, dele = cur, torch.empty(0, dtype=torch.int64, device=self.device)

@@ -25,8 +25,13 @@ PACK_META = os.environ.get("STG_PACK_META", "1") != "0"
 MAX_META_REPACKS = 16
 
 
-def _edges_to_device(edge_list, device):
-    """Accept a list of (src,dst) tuples, an [E,2] numpy/torch array or a (src,dst) pair of arrays."""
+def _edges_to_device(edge_list, device, num_nodes=None):
+    """Accept a list of (src,dst) tuples, an [E,2] numpy/torch array or a (src,dst) pair of arrays.
+
+    With ``num_nodes`` every id is checked against ``[0, num_nodes)`` BEFORE the cast to int32 (one host read-back,
+    at construction): the radix sort of ``stg_csr_build`` / ``stg_snapshot_keys_from_edges`` only covers the key
+    bits of valid ids, so an id >= num_nodes (``num_nodes`` passed as max id instead of max id + 1), a negative id
+    or an int64 id that does not fit would otherwise corrupt the row-offset fill silently."""
     if isinstance(edge_list, tuple) and len(edge_list) == 2 and not np.isscalar(edge_list[0]) \
             and len(np.shape(edge_list[0])) == 1 and len(edge_list[0]) != 2:
         src, dst = edge_list
@@ -39,8 +44,16 @@ def _edges_to_device(edge_list, device):
             e = torch.from_numpy(np.asarray(edge_list, dtype=np.int64).reshape(-1, 2))
         e = e.reshape(-1, 2)
         src, dst = e[:, 0], e[:, 1]
-    src = src.to(device=device, dtype=torch.int32).contiguous()
-    dst = dst.to(device=device, dtype=torch.int32).contiguous()
+    if src.is_floating_point() or dst.is_floating_point() or src.dtype == torch.bool:
+        raise TypeError("vertex ids must be integers")
+    src, dst = src.to(device=device), dst.to(device=device)
+    if num_nodes is not None and src.numel() > 0:
+        lo = int(torch.minimum(src.min(), dst.min()))
+        hi = int(torch.maximum(src.max(), dst.max()))
+        if lo < 0 or hi >= int(num_nodes):
+            raise ValueError(f"vertex ids must lie in [0, {int(num_nodes)}): found ids in [{lo}, {hi}]")
+    src = src.to(dtype=torch.int32).contiguous()
+    dst = dst.to(dtype=torch.int32).contiguous()
     return src, dst
 
 

@@ -31,7 +31,7 @@ class StaticGraph(STGraphBase):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._num_nodes = int(num_nodes)
 
-        src, dst = _edges_to_device(edge_list, self.device)
+        src, dst = _edges_to_device(edge_list, self.device, self._num_nodes)
         self._forward_graph, self._backward_graph, _, n_unique = build_csr_pair(src, dst, self._num_nodes)
         # static_graph.py:49 -> len(set(edge_list))
         self._num_edges = int(n_unique.item())

@@ -38,7 +38,29 @@ class GCNConv(nn.Module):
         if self.bias is not None:
             nn.init.zeros_(self.bias)
 
+    def _forward_partitioned(self, graph, h: Tensor, edge_weight: Tensor | None) -> Tensor:
+        """``graph`` is a :class:`stgraph_b200.dist.PartitionedGraph`: ``h`` and the result hold this rank's rows."""
+        from ....dist.partition import partitioned_gcn_aggregate
+
+        if edge_weight is not None:
+            raise NotImplementedError("edge_weight is not supported on a PartitionedGraph")
+        norm = graph.get_ndata("norm")
+        if norm is None:
+            raise KeyError("PartitionedGraph passed to GCNConv forward pass does not contain 'norm' node data")
+        if (len(norm.shape) != SizeConstants.NODE_NORM_SIZE.value or norm.shape[1] != 1
+                or norm.shape[0] != graph.num_local_nodes()):
+            raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_local_nodes, 1)")
+        h = torch.mm(h, self.weight)
+        h = partitioned_gcn_aggregate(graph, h, norm)
+        if self.bias is not None:
+            h = h + self.bias
+        if self.activation:
+            h = self.activation(h)
+        return h
+
     def forward(self, graph, h: Tensor, edge_weight: Tensor | None = None) -> Tensor:
+        if hasattr(graph, "num_local_nodes"):          # row-partitioned graph (multi-GPU): local rows in, local rows out
+            return self._forward_partitioned(graph, h, edge_weight)
         norm = graph.get_ndata("norm")
         if norm is None:
             raise KeyError("StaticGraph passed to GCNConv forward pass does not contain 'norm' node data")

@@ -185,3 +185,29 @@ def test_pcsr_fixture_exercises_readd_and_mass_delete(gp):
     gone = (sets[0] - sets[1]) & sets[3]
     assert gone, "an edge is deleted and re-added later"
     assert min(len(s) for s in sets) <= 3 < max(len(s) for s in sets)
+
+
+# ---- a9: the reference's own DynamicGraph._preprocess_graph_structure (dynamic_graph.py:56-79) -----------------
+def _update_streams():
+    g = np.load(os.path.join(GOLD, "ref_updates.npz"))
+    for tag in ("a", "b", "c"):
+        sizes, flat, n = g[f"{tag}/snap_sizes"], g[f"{tag}/snap_edges"], int(g[f"{tag}/num_nodes"])
+        snaps, o = [], 0
+        for sz in sizes:
+            snaps.append(flat[o:o + sz])
+            o += sz
+        yield tag, g, snaps, n
+
+
+def test_snapshot_update_oracle_equals_reference_preprocessing():
+    """oracle/structure.py:snapshot_updates == the add / delete lists the reference's pure-Python preprocessing builds."""
+    from oracle import structure as S
+
+    for tag, g, snaps, n in _update_streams():
+        ups = S.snapshot_updates(snaps)
+        for t in range(len(snaps)):
+            for kind in ("add", "delete"):
+                ref = g[f"{tag}/{t}/{kind}"]
+                np.testing.assert_array_equal(ref[:, 0], ups[t][kind][0], err_msg=f"{tag} t={t} {kind} src")
+                np.testing.assert_array_equal(ref[:, 1], ups[t][kind][1], err_msg=f"{tag} t={t} {kind} dst")
+        assert sum(g[f"{tag}/{t}/delete"].shape[0] for t in range(1, len(snaps))) > 0

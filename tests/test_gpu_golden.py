@@ -189,3 +189,25 @@ def test_pcsr_graph_equals_reference_pcsr(cuda, gp, tag):
         same(G._backward_graph, f"{tag}/bwd/{t}")
         if t < T - 1:
             same(G._backward_graph, f"{tag}/rewind/{t}")
+
+
+@pytest.mark.parametrize("kind", ["naive", "pcsr", "gpma"])
+def test_graph_updates_equal_reference_preprocessing(cuda, kind):
+    """a9: ``graph_updates[t]`` built on the GPU (csrc/snapshot.cu) == the reference's own
+    ``DynamicGraph._preprocess_graph_structure`` output (tests/golden/ref_updates.npz), bit for bit, in its order."""
+    from stgraph_b200.graph import GPMAGraph, NaiveGraph, PCSRGraph
+
+    g = np.load(os.path.join(GOLD, "ref_updates.npz"))
+    for tag in ("a", "b", "c"):
+        sizes, flat, n = g[f"{tag}/snap_sizes"], g[f"{tag}/snap_edges"], int(g[f"{tag}/num_nodes"])
+        snaps, o = [], 0
+        for sz in sizes:
+            snaps.append(flat[o:o + sz])
+            o += sz
+        G = {"naive": NaiveGraph, "pcsr": PCSRGraph, "gpma": GPMAGraph}[kind](snaps, n)
+        for t in range(len(snaps)):
+            for what in ("add", "delete"):
+                got = G.graph_updates[str(t)][what].cpu().numpy().astype(np.int64)
+                ref = g[f"{tag}/{t}/{what}"]
+                np.testing.assert_array_equal(got & 0xFFFFFFFF, ref[:, 0], err_msg=f"{tag} t={t} {what} src")
+                np.testing.assert_array_equal(got >> 32, ref[:, 1], err_msg=f"{tag} t={t} {what} dst")

@@ -458,3 +458,37 @@ def test_gru_gate_ops_extreme_inputs(cuda):
     assert torch.isfinite(out).all() and torch.allclose(out, z * h + (1 - z) * torch.tanh(0.5 * big), rtol=1e-5, atol=1e-7)
     a = torch.tensor([[-3e6, -1e6, 0.5, 1e6, 3e6]], device=cuda)
     assert torch.equal(bias_clamp(a.clone(), None, -1e6, 1e6), torch.clamp(a, -1e6, 1e6))
+
+
+def test_state_stack_does_not_grow_without_a_backward(cuda):
+    """forward calls under no_grad / on inputs that need no gradient must not push on the LIFO stacks."""
+    from stgraph_b200.nn.pytorch import GCNConv
+
+    g, _, _ = _graph(200, 1500, 5, cuda)
+    g.set_ndata("norm", g.degree_norm())
+    layer = GCNConv(8, 8).to(cuda)
+    x = torch.randn(200, 8, device=cuda)
+    with torch.no_grad():
+        for _ in range(5):
+            layer(g, x)
+    ctx = next(iter(layer.stgraph._ctx_map.values()))
+    stack = ctx._executor_cache.ts.tensor_map_stack
+    assert len(stack) == 0
+    y = layer(g, x)                       # weights need a gradient: one entry, popped by backward
+    assert len(stack) == 1
+    y.sum().backward()
+    assert len(stack) == 0
+
+
+def test_fused_clamp_propagates_nan_like_torch(cuda):
+    from stgraph_b200 import ops_gru
+
+    a = torch.tensor([[1.0, float("nan"), 2e6, -3e6]], device=cuda)
+    ref = torch.clamp(a.clone(), -1e6, 1e6)
+    a2 = a.clone().requires_grad_(True)
+    got = ops_gru.bias_clamp(a2 * 1.0, None, -1e6, 1e6)
+    assert torch.equal(torch.isnan(got), torch.isnan(ref)) and torch.equal(got[~torch.isnan(got)], ref[~torch.isnan(ref)])
+    got.backward(torch.ones_like(got))
+    a3 = a.clone().requires_grad_(True)
+    torch.clamp(a3 * 1.0, -1e6, 1e6).backward(torch.ones_like(a3))
+    assert torch.equal(a2.grad, a3.grad)

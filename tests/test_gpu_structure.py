@@ -117,3 +117,21 @@ def test_degree_norm(cuda):
     got = g.degree_norm().cpu().reshape(-1)
     assert got.shape == (n,)
     torch.testing.assert_close(got, ref, rtol=2e-7, atol=0)
+
+
+def test_out_of_range_vertex_ids_are_rejected(cuda):
+    """ids are validated against num_nodes before the int32 cast (the sort covers valid key bits only)."""
+    from stgraph_b200.graph import GPMAGraph, StaticGraph
+
+    with pytest.raises(ValueError, match="vertex ids"):
+        StaticGraph([(0, 1), (2, 5)], None, 5)                    # num_nodes given as the max id
+    with pytest.raises(ValueError, match="vertex ids"):
+        StaticGraph(torch.tensor([[0, 1], [-1, 2]]), None, 5)
+    with pytest.raises(ValueError, match="vertex ids"):
+        StaticGraph(torch.tensor([[0, 1], [(1 << 32) + 1, 2]], dtype=torch.int64), None, 5)     # would wrap to 1 as int32
+    with pytest.raises(ValueError, match="vertex ids"):
+        GPMAGraph([[(0, 1)], [(0, 7)]], 5)
+    with pytest.raises(TypeError):
+        StaticGraph(torch.tensor([[0.0, 1.0]]), None, 5)
+    g = StaticGraph([(0, 1), (2, 4)], None, 5)
+    assert g.get_num_edges() == 2
