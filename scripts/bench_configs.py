@@ -196,53 +196,100 @@ def config3():
 
 
 # ------------------------------------------------------------------ config 4: dynamic TGCN on GPMAGraph
+class DynTGCN(torch.nn.Module):
+    """``benchmarking/dynamic-temporal-tgcn/seastar/model.py:5-21`` with the decode as one fused kernel."""
+
+    def __init__(self, node_features, hidden):
+        super().__init__()
+        self.temporal = TGCN(node_features, hidden)
+        self.linear = torch.nn.Linear(hidden, node_features)
+
+    def forward(self, g, x, w, h):
+        h = self.temporal(g, x, w, h)
+        return self.linear(F.relu(h)), h
+
+    def decode(self, z, edge_label_index):
+        from stgraph_b200.ops_decode import edge_dot
+
+        return edge_dot(z, edge_label_index, check=False)
+
+
 def config4(scale=1.0):
+    """N = 10^6, a stream of 2*10^7 DISTINCT power-law edges, window base = 10^7, slide 10^5
+    => 100 snapshots of 10^7 live edges with +-10^5 per step; STGraphTGCN(32, 64), link-prediction decode + BCE,
+    backprop every 20 (``dynamic-temporal-tgcn/seastar/train.py:189-231``), GPMAGraph."""
     n = int(1_000_000 * scale)
     base, slide, T = int(10_000_000 * scale), int(100_000 * scale), 100
-    src, dst = synthetic.temporal_stream(n, base + slide * (T - 1), alpha=1.8, seed=0, device=dev)
+    src, dst = synthetic.temporal_stream(n, base + slide * (T - 1), alpha=1.8, seed=0, device=dev, distinct=True,
+                                         max_frac=2e-4)
     snaps = synthetic.sliding_window_snapshots(src, dst, base, slide, T)
     snaps = [torch.stack([s, d_], 1) for s, d_ in snaps]
     res = {"num_nodes": n, "snapshots": len(snaps)}
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     G = GPMAGraph(snaps, n)
     torch.cuda.synchronize()
     res["gpma_construct_s"] = time.perf_counter() - t0
+    del snaps, src, dst
     res["edges_t0"] = G.get_num_edges()
     res["adds_per_step"] = int(G.graph_updates["1"]["add"].shape[0])
     res["deletes_per_step"] = int(G.graph_updates["1"]["delete"].shape[0])
     # structure update cost per snapshot (apply + forward view + hub schedule), device time
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    T_ = len(G.graph_updates)
     G.reset_graph()
+    G.get_graph(0)
     a.record()
-    for t in range(1, len(snaps)):
+    for t in range(1, T_):
         G.get_graph(t)
     b.record()
     torch.cuda.synchronize()
-    res["gpma_update_ms_per_snapshot"] = a.elapsed_time(b) / (len(snaps) - 1)
+    res["gpma_update_ms_per_snapshot"] = a.elapsed_time(b) / (T_ - 1)
     u = res["adds_per_step"] + res["deletes_per_step"]
-    res["gpma_update_alg_bytes"] = 12 * u + 12 * res["edges_t0"] + 8 * n
-    # TGCN(32, 64) over the snapshots, backprop every 20 (dynamic-temporal-tgcn/seastar/train.py:189-231)
+    res["gpma_update_alg_bytes"] = 12 * u + 12 * res["edges_t0"] + 8 * n       # SURVEY.md section 8(d), S_touched = |S|
+    res["gpma_update_alg_gbs"] = res["gpma_update_alg_bytes"] / (res["gpma_update_ms_per_snapshot"] * 1e-3) / 1e9
+    # link-prediction pairs per timestamp: the edges that appear at t+1 (positives) and as many random pairs
+    # (preprocess_temporal_data.py:74-86), targets 1 / 0
+    gen = torch.Generator(device=dev).manual_seed(5)
+    pairs, targets = [], []
+    for t in range(T_ - 1):
+        add = G.graph_updates[str(t + 1)]["add"]
+        pos = torch.stack([add & 0xFFFFFFFF, add >> 32])
+        neg = torch.randint(0, n, (2, pos.shape[1]), device=dev, generator=gen)
+        pairs.append(torch.cat([pos, neg], 1).contiguous())
+        targets.append(torch.cat([torch.ones(pos.shape[1], device=dev), torch.zeros(pos.shape[1], device=dev)]))
+    res["decode_pairs_per_step"] = int(pairs[0].shape[1])
     torch.manual_seed(0)
-    model = TGCN(32, 64, fused=True).to(dev)
+    model = DynTGCN(32, 64).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2)
-    x = torch.randn(n, 32, device=dev)
+    criterion = torch.nn.BCEWithLogitsLoss()
+    every = 20
 
     def epoch(graph):
         graph.reset_graph()
-        h = None
-        cost = 0
-        for t in range(len(snaps)):
-            graph.get_graph(t)
-            graph.set_ndata("norm", graph.degree_norm())
-            h = model(graph, x, None, h)
-            cost = cost + (h ** 2).mean()
-            if (t + 1) % 20 == 0:
-                opt.zero_grad()
-                cost.backward()
-                opt.step()
-                h, cost = h.detach(), 0
+        for index in range((T_ + every - 1) // every):
+            opt.zero_grad()
+            cost, h = 0, None
+            y_hat = torch.randn(n, 32, device=dev)
+            graph.get_graph(index * every)
+            for k in range(every):
+                t = index * every + k
+                if t >= T_ - 1:
+                    break
+                graph.get_graph(t)
+                graph.set_ndata("norm", graph.degree_norm())
+                y_hat, h = model(graph, y_hat, None, h)
+                cost = cost + criterion(model.decode(y_hat, pairs[t]), targets[t])
+            if isinstance(cost, int):
+                break
+            cost = cost / (every + 1)
+            cost.backward()
+            opt.step()
+        return float(cost) if not isinstance(cost, int) else None
 
+    l0 = kernels.launch_count
     res["tgcn_gpma_epoch_ms"] = timed(lambda: epoch(G), warm=1, reps=2)
+    res["our_kernel_launches_per_epoch"] = (kernels.launch_count - l0) / 3
     out["config4_dynamic_tgcn"] = res
 
 

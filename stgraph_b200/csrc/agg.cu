@@ -53,7 +53,6 @@ struct AggParams {
   const int32_t* __restrict__ hub_count;
   const int32_t* __restrict__ out_rows;   // view row -> output row (NULL: identity)
   const int2* __restrict__ meta;          // PACKED mode: {column, scale bits} of every CSR slot (stg_csr_pack_edge_meta_f32)
-  int far_window;                         // > 0: sources further than this from the row are fetched with an L2 evict_first hint
   int* queue;                             // global row queue {next chunk, finished blocks} (StgCsrView::work_queue) or NULL
   int num_rows;
   int num_edges;
@@ -303,21 +302,12 @@ __device__ __forceinline__ float4 shfl_xor_vec<float4>(float4 v, int o) {
 // L2 evict_last policy 4.80-4.85 ms (noise), no L1 allocation 6.24 ms (the 7 % of sectors that hit L1 matter).
 __device__ __forceinline__ float4 ldg_row(const float4* p) { return __ldg(p); }
 
-// L2 eviction hints (HINT): on a graph with community structure most sources of a row lie in a window of ids around
-// it and are re-read from L2 by the neighbouring rows, while the far ("random") 10 % of the edges stream 2.5 GB of
-// rows through L2 that nobody reads again.  Far sources are fetched evict_first, near ones evict_last, selected
-// per edge without a branch (the policy is a 64-bit register operand of ld.global.L2::cache_hint).
-__device__ __forceinline__ float4 ldg_row_hint(const float4* p, unsigned long long policy) {
-  float4 v;
-  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "l"(p), "l"(policy));
-  return v;
-}
-
-template <int UNROLL, int MODE, bool HINT = false>
+// (Measured and dropped, r2: per-edge L2 eviction hints -- ld.global.L2::cache_hint with an evict_first policy for
+// sources further than a window of ids from the row, evict_last for the near ones, selected without a branch --
+// 2.22-2.32 ms against 2.15 ms on config 5: the policy select costs more issue slots than the hit rate returns.)
+template <int UNROLL, int MODE>
 __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int beg, int end, int lane, float4& result,
-                                                      int my_c, float my_m, float my_s, int row = 0) {
+                                                      int my_c, float my_m, float my_s) {
   static_assert(UNROLL % 2 == 0, "two edges per step");
   constexpr int STEPS = UNROLL / 2;
   const int half = lane >> 4;
@@ -334,25 +324,10 @@ __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int be
     base1 = reinterpret_cast<const char*>(p.x + o1);
   }
   const bool live1 = (hl + 16) * 4 < p.width;   // chunk 0 is always inside the row (width > 64); F=100: 9 of 16 lanes
-  unsigned long long pol_far = 0, pol_near = 0;
-  if constexpr (HINT) {
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_far));
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_near));
-  }
-  auto policy = [&](int c) { return (abs(c - row) > p.far_window) ? pol_far : pol_near; };
-  auto row0 = [&](int c) {
-    const float4* a = reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes);
-    if constexpr (HINT) return ldg_row_hint(a, policy(c));
-    else return ldg_row(a);
-  };
+  auto row0 = [&](int c) { return ldg_row(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
   auto row1 = [&](int c) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* a = reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes);
-    if constexpr (HINT) {
-      if (live1) v = ldg_row_hint(a, policy(c));
-    } else {
-      if (live1) v = ldg_row(a);
-    }
+    if (live1) v = ldg_row(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
     return v;
   };
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
@@ -480,7 +455,7 @@ __device__ __forceinline__ void prefetch_row(const AggParams& p, int row, int gl
 // rows (4736 warps x 8 rows = 38 K rows, 15 MB of x on config 5, against the 151 K-row window of 592 resident
 // 256-row blocks), so the source rows of a community graph are re-read from L2, not from HBM, and no block
 // waits for its longest row at the tail.  The last block to finish resets the counters for the next launch.
-template <int VEC, int GROUP, int NACC, int MINB, int UNROLL, int MODE, bool PAIR = false, bool GQ = false, bool HINT = false>
+template <int VEC, int GROUP, int NACC, int MINB, int UNROLL, int MODE, bool PAIR = false, bool GQ = false>
 __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(const AggParams p, int slots_per_block) {
   using T = typename VecT<VEC>::type;
   constexpr int GPW = 32 / GROUP;
@@ -577,7 +552,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) agg_rows_pipe_kernel(cons
       }
       if constexpr (PAIR) {
         static_assert(VEC == 4 && GROUP == 32 && NACC == 1, "pair form: one row per warp, float4 lanes");
-        accumulate_edges_pair<UNROLL, MODE, HINT>(p, beg0, end0, lane, acc[0], c0, 0.f, s0, slot0);
+        accumulate_edges_pair<UNROLL, MODE>(p, beg0, end0, lane, acc[0], c0, 0.f, s0);
       } else {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) zero_vec(acc[k]);
@@ -766,15 +741,6 @@ inline int queue_chunk() {
   return v;
 }
 
-// Sources further than this many ids from their row get the L2 evict_first hint (STG_AGG_FAR; 0 = no hints; read once).
-inline int far_window() {
-  static const int v = [] {
-    const char* e = getenv("STG_AGG_FAR");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
-
 template <int VEC, int GROUP, int NACC, int MODE>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
@@ -784,7 +750,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   const bool hubs = p.hub_threshold > 0 && p.hub_rows != nullptr;
   // Small graphs gain nothing from the overlap and a programmatic edge costs extra inside a captured CUDA
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
-  const bool overlap = hubs && p.num_edges >= (1 << 20);
+  const bool overlap = hubs && p.num_edges >= (1 << 18);
   if (hubs) {
     agg_hub_kernel<VEC, GROUP, NACC, MODE><<<2 * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
@@ -809,10 +775,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
       const int gblocks = std::min(sm_count() * MINB, (p.num_rows + 7) / 8);
       if constexpr (VEC == 4 && NACC == 1) {
         if (p.width > 64 && pair_mode()) {
-          if (gq && p.far_window > 0 && MODE != kParts) {
-            STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true, true, true>, gblocks,
-                                       kBlockThreads, stream, overlap, p, queue_chunk()));
-          } else if (gq) {
+          if (gq) {
             STG_CUDA(launch_overlapped(agg_rows_pipe_kernel<VEC, GROUP, NACC, MINB, 8, MODE, true, true>, gblocks, kBlockThreads,
                                        stream, overlap, p, queue_chunk()));
           } else {
@@ -889,7 +852,6 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   p.out_rows = out_rows;
   p.meta = reinterpret_cast<const int2*>(meta);
   p.queue = g->work_queue;
-  p.far_window = far_window();
   p.accumulate = accumulate;
   p.nparts = nparts;
   for (int q = 0; q < STG_MAX_PARTS; ++q) p.xs[q] = q < nparts ? parts[q] : nullptr;

@@ -3,11 +3,12 @@
 One :class:`HaloExchange` serves one CSR direction of a :class:`~stgraph_b200.dist.partition.PartitionedGraph`
 at one feature width.  Per aggregation (``aggregate``):
 
-    side stream (high priority)                          main stream
+    copy streams (owned by the C handle)                  my stream
     -----------------------------------------------      -------------------------------------------------
-    gather the rows my peers need into a send buffer      own-source pass: every local row, edges whose
-    P-1 copy-engine copies into the peers' halo buffers     source row I own (packed {col, scale} metadata,
-    post an arrival flag on every peer                      global row queue)  ->  out = ...
+                                                          P-1 gather kernels: the rows peer q needs -> send buffer
+    copy q's segment into q's halo buffer, then a         own-source pass: every local row, edges whose
+      4-byte arrival flag, as soon as it is packed          source row I own (packed {col, scale} metadata,
+      (copy engines; P-1 copies on 3 streams)               global row queue)  ->  out = ...
                                                           wait for the P-1 arrival flags (one spinning warp)
                                                           halo-source pass: rows with a remote neighbour,
                                                             out += ... (row-subset form)
@@ -89,6 +90,8 @@ class HaloExchange:
             within = torch.arange(n_send, device=dev, dtype=torch.int64) - seg[peer]
             self._send_peer = peer.to(torch.int32).contiguous()
             self._send_slot = (torch.as_tensor(dst_off, dtype=torch.int64, device=dev)[peer] + within).contiguous()
+        self._handle = ctypes.c_void_p()
+        _lib.call("stg_exchange_create", int(os.environ.get("STG_COPY_STREAMS", "3")), ctypes.byref(self._handle))
         self.side = torch.cuda.Stream(device=dev, priority=-1)
         self._ev_in = torch.cuda.Event()
         self._ev_gathered = torch.cuda.Event()
@@ -100,6 +103,11 @@ class HaloExchange:
         self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, None, device=dev)
                           if plan.halo_cols.numel() else None)
         self.ns_own, self.ns_halo = ns_own, ns_halo
+        # which leg is longer?  exchange: halo bytes in at ~600 GB/s; own-source pass: ~25 edges/ns (measured, F=100)
+        t_x = max(plan.n_halo, n_send) * self.feat * 4 / 600e9
+        t_own = int(plan.own_cols.numel()) * (self.feat / 100.0) / 25e9
+        gf = os.environ.get("STG_GATHER_FIRST")
+        self.gather_first = (t_x > 0.8 * t_own) if gf is None else gf == "1"
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:
@@ -119,38 +127,37 @@ class HaloExchange:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)] if self.profile is not None else None
         if ev:
             ev[0].record(cur)
-        self._ev_in.record(cur)
-        side.wait_event(self._ev_in)
+            ev[4].record(cur)
         n_send = int(plan.send_index.numel())
-        with torch.cuda.stream(side):
-            if ev:
-                ev[4].record(side)
-            if self.mode == "sm":
+        if self.mode == "sm":
+            self._ev_in.record(cur)
+            side.wait_event(self._ev_in)
+            with torch.cuda.stream(side):
                 if n_send:
                     _lib.call("stg_halo_push_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(),
                               self._send_peer.data_ptr(), self._send_slot.data_ptr(), n_send, self._peer_halo[k], world,
                               self.push_blocks, side.cuda_stream)
-                self._ev_gathered.record(side)
                 _lib.call("stg_peer_signal", self._peer_flag[k], world, rank, it & 0xFFFF, side.cuda_stream)
-            elif ev:          # profiling: the three steps one by one, with an event between them
-                _lib.call("stg_rows_gather_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), n_send,
-                          self.send_buf.data_ptr(), self.gather_blocks, side.cuda_stream)
                 self._ev_gathered.record(side)
-                ev[5].record(side)
-                _lib.call("stg_halo_send_f32", self.send_buf.data_ptr(), self.feat, world, rank, self._send_off,
-                          self._peer_dst[k], side.cuda_stream)
-                ev[6].record(side)
-                _lib.call("stg_halo_exchange_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), self._zero_off,
-                          self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(), it & 0xFFFF,
-                          world, rank, self.gather_blocks, side.cuda_stream)        # no rows: the flag copies only
-            else:
-                _lib.call("stg_halo_exchange_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), self._send_off,
-                          self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(), it & 0xFFFF,
-                          world, rank, self.gather_blocks, side.cuda_stream)
-                self._ev_gathered.record(side)
+                if ev:
+                    ev[5].record(side)
+                    ev[6].record(side)
+        else:
+            # per-peer gathers, copies + flags on the handle's copy streams.  When the exchange is the longer leg (8
+            # ranks) the gathers run on MY stream and finish before the aggregation pass starts (0.06 ms with the
+            # whole chip); when the own-source pass is the longer leg (2-4 ranks) they run beside it on a side stream.
+            gs = cur if self.gather_first else side
+            if not self.gather_first:
+                self._ev_in.record(cur)
+                side.wait_event(self._ev_in)
+            _lib.call("stg_exchange_run_f32", self._handle, x_own.data_ptr(), self.feat, plan.send_index.data_ptr(),
+                      self._send_off, self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(),
+                      it & 0xFFFF, world, rank, gs.cuda_stream)
             if ev:
-                ev[7].record(side)
-        # main stream: the edges whose source I own
+                ev[5].record(gs)
+                _lib.call("stg_exchange_join", self._handle, side.cuda_stream)
+                ev[6].record(side)
+        # the edges whose source I own
         if self.meta_own is not None:
             kernels.agg_packed_sum_rows(self.v_own, self.meta_own, None, x_own, rs, out, accumulate=False)
         else:
@@ -164,8 +171,11 @@ class HaloExchange:
         if self.meta_halo is not None:
             kernels.agg_packed_sum_rows(self.v_halo, self.meta_halo, plan.halo_out_rows, self.halo_rows(k), rs, out,
                                         accumulate=True)
-        cur.wait_event(self._ev_gathered)          # x_own may be reused by the caller from here on
-        kernels.launch_count += 3                  # gather (or push) + signal + wait kernels of this call
+        if self.mode == "sm":
+            cur.wait_event(self._ev_gathered)      # x_own may be reused by the caller from here on
+        else:
+            _lib.call("stg_exchange_join", self._handle, cur.cuda_stream)     # my copies have drained: send_buf is free
+        kernels.launch_count += 2 + (world - 1 if self.mode != "sm" else 1)   # gathers (or push + signal) + wait kernel
         if ev:
             ev[3].record(cur)
             self.profile.append(ev)
@@ -180,10 +190,17 @@ class HaloExchange:
     def profile_summary(self):
         """Mean device time (ms) of the segments of ``aggregate`` (set ``self.profile = []`` to collect)."""
         torch.cuda.synchronize()
-        seg = {"own_pass": (0, 1), "wait_flags": (1, 2), "halo_pass": (2, 3), "total": (0, 3), "gather": (4, 5),
-               "send": (5, 6), "signal": (6, 7), "side_total": (4, 7)}
-        if self.mode == "sm":
-            seg.pop("gather"), seg.pop("send")
-            seg["push"] = (4, 6)
+        seg = {"gather_or_push": (4, 5), "own_pass": (5, 1), "wait_flags": (1, 2), "halo_pass": (2, 3), "total": (0, 3),
+               "sends_done_after_start": (4, 6)}
+        if self.mode == "sm" or not self.gather_first:
+            seg["own_pass"] = (0, 1)
         n = max(len(self.profile), 1)
         return {name: sum(e[a].elapsed_time(e[b]) for e in self.profile) / n for name, (a, b) in seg.items()}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _lib.call("stg_exchange_destroy", self._handle)
+                self._handle = None
+        except Exception:
+            pass

@@ -15,6 +15,8 @@ Plan construction is torch plumbing (unique / searchsorted, one-time); the per-s
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -85,14 +87,25 @@ class HaloPlan:
         self._keep = []
 
     # ------------------------------------------------------- overlapped two-pass form
+    @staticmethod
+    def hub_threshold_for(n_edges: int) -> int:
+        """Rows longer than this go to the block-per-row kernel.  One warp walks a row at ~8 edges per memory round
+        trip, so the longest warp-owned row bounds the launch from below: 1024 edges (~0.1 ms) are invisible in the
+        2 ms pass over the whole graph but a third of a 0.3 ms pass over one rank's share of an 8-way partition, and
+        more than the whole halo-source pass (ncu, r2: 23 % of the warp samples of that pass sat at the final barrier
+        behind one long row).  Scale the threshold with the work of the launch."""
+        per = int(os.environ.get("STG_HUB_EDGES_PER_UNIT", "30000"))      # A/B knob
+        return int(min(HUB_THRESHOLD, max(64, n_edges // max(per, 1))))
+
     def _make_view(self, ro, cols, eids, n_rows=None):
         dev = ro.device
         n_rows = self.n_rows if n_rows is None else n_rows
         n_e = int(cols.shape[0])
-        cap = n_e // max(HUB_THRESHOLD, 1) + 1
+        threshold = self.hub_threshold_for(n_e)
+        cap = n_e // max(threshold, 1) + 1
         hub_rows = torch.empty(cap, dtype=torch.int32, device=dev)
         hub_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.call("stg_csr_hub_rows", ro.data_ptr(), n_rows, HUB_THRESHOLD, hub_rows.data_ptr(), cap,
+        _lib.call("stg_csr_hub_rows", ro.data_ptr(), n_rows, threshold, hub_rows.data_ptr(), cap,
                   hub_count.data_ptr(), _lib.current_stream_ptr())
         has_hubs = int(hub_count.item()) > 0
         self._keep.append((hub_rows, hub_count))
@@ -107,7 +120,7 @@ class HaloPlan:
         v.eids_identity = 0
         v.hub_rows = hub_rows.data_ptr() if has_hubs else None
         v.hub_count = hub_count.data_ptr() if has_hubs else None
-        v.hub_threshold = HUB_THRESHOLD if has_hubs else 0
+        v.hub_threshold = threshold if has_hubs else 0
         v.hub_capacity = cap if has_hubs else 0
         queue = torch.zeros(2, dtype=torch.int32, device=dev)      # global row queue of the aggregation kernel
         self._keep.append(queue)

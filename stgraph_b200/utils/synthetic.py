@@ -186,13 +186,29 @@ def products_shaped(seed: int = 0, device="cpu", scale: float = 1.0, locality: f
             "locality": locality, "window": window}
 
 
-def temporal_stream(num_nodes: int, num_events: int, alpha: float = 1.8, seed: int = 0, device="cpu"):
+def temporal_stream(num_nodes: int, num_events: int, alpha: float = 1.8, seed: int = 0, device="cpu",
+                    distinct: bool = False, max_frac: float | None = None):
     """Config 4 input: exactly ``num_events`` temporal edges with Zipf endpoints, no self loops
-    (sx-mathoverflow / wiki-talk shaped; repeated interactions are frequent, snapshots de-duplicate them)."""
+    (sx-mathoverflow / wiki-talk shaped; repeated interactions are frequent, snapshots de-duplicate them).
+
+    ``distinct=True``: every (src, dst) pair occurs once in the stream, in random order, so that a sliding window of
+    ``base`` events holds exactly ``base`` live edges and every slide adds and deletes exactly ``slide`` of them
+    (~10^7 live edges, +-10^5 per step); ``max_frac`` caps the share of the endpoints one
+    vertex may take (a Zipf(1.8) head vertex would otherwise need more distinct partners than there are vertices)."""
     g = _gen(seed, device)
-    w = _zipf_weights(num_nodes, alpha, None, g, device)
+    w = _zipf_weights(num_nodes, alpha, max_frac, g, device)
     cdf = torch.cumsum(w, 0)
     cdf = cdf / cdf[-1]
+    if distinct:
+        keys = torch.empty(0, dtype=torch.int64, device=device)
+        while keys.shape[0] < num_events:
+            k = int((num_events - keys.shape[0]) * 1.3) + 4096
+            u = _sample(cdf, k, g, device)
+            v = _sample(cdf, k, g, device)
+            keep = u != v
+            keys = torch.unique(torch.cat([keys, u[keep] * num_nodes + v[keep]]))
+        keys = keys[torch.randperm(keys.shape[0], generator=g, device=device)[:num_events]]
+        return (keys // num_nodes).to(torch.int32), (keys % num_nodes).to(torch.int32)
     us, vs, have = [], [], 0
     while have < num_events:
         k = int((num_events - have) * 1.05) + 1024

