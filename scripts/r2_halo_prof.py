@@ -43,6 +43,33 @@ def mkview(ro, cols, n_rows):
     return v
 
 
+def mkview_hub(ro, cols, n_rows, threshold):
+    v = mkview(ro, cols, n_rows)
+    if threshold > 0:
+        cap = int(cols.shape[0]) // threshold + 1
+        hr = torch.empty(cap, dtype=torch.int32, device=dev)
+        hc = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("stg_csr_hub_rows", ro.data_ptr(), n_rows, threshold, hr.data_ptr(), cap, hc.data_ptr(), _lib.current_stream_ptr())
+        nh = int(hc.item())
+        keep.append((hr, hc))
+        if nh > 0:
+            v.hub_rows, v.hub_count, v.hub_threshold, v.hub_capacity = hr.data_ptr(), hc.data_ptr(), threshold, cap
+        return v, nh
+    return v, 0
+
+
+def timeit(fn, reps=20):
+    for _ in range(4):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 rank = 0
 lo, hi = bounds[rank], bounds[rank + 1]
 ro = csr.row_offset[lo:hi + 1].long()
@@ -57,21 +84,26 @@ sel = torch.nonzero(cnt > 0).reshape(-1)
 cro = torch.zeros(sel.numel() + 1, dtype=torch.int32, device=dev)
 cro[1:] = torch.cumsum(cnt[sel], 0).int()
 hcols = torch.searchsorted(halo_ids, cols[~local]).int().contiguous()
-v_halo = mkview(cro, hcols, int(sel.numel()))
+ocnt = torch.bincount(rows[local], minlength=nr)
+oro = torch.zeros(nr + 1, dtype=torch.int32, device=dev)
+oro[1:] = torch.cumsum(ocnt, 0).int()
+ocols = (cols[local] - lo).int().contiguous()
 halo = x[halo_ids].contiguous()
+x_own = x[lo:hi].contiguous()
 ns_halo = norm[halo_ids].contiguous()
-rs = norm[lo:hi].contiguous()
+ns_own = norm[lo:hi].contiguous()
+rs = ns_own
 out = torch.randn(nr, F, device=dev)
-meta = kernels.pack_edge_meta(v_halo, ns_halo, None, device=dev)
 out_rows = sel.int().contiguous()
-print("rows", nr, "rows with halo", int(sel.numel()), "halo edges", int(hcols.numel()), "halo rows", int(halo_ids.numel()))
-for _ in range(4):
-    kernels.agg_packed_sum_rows(v_halo, meta, out_rows, halo, rs, out, accumulate=True)
-torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(10):
-    kernels.agg_packed_sum_rows(v_halo, meta, out_rows, halo, rs, out, accumulate=True)
-b.record()
-torch.cuda.synchronize()
-print("halo pass ms", a.elapsed_time(b) / 10)
+print("P", P, "rows", nr, "rows with halo", int(sel.numel()), "halo edges", int(hcols.numel()), "halo rows", int(halo_ids.numel()),
+      "own edges", int(ocols.numel()), "max halo deg", int(cnt.max()), "chunk", os.environ.get("STG_AGG_CHUNK", "4"))
+for t in (0, 32, 64, 128, 256, 1024):
+    v_halo, nh = mkview_hub(cro, hcols, int(sel.numel()), t)
+    meta = kernels.pack_edge_meta(v_halo, ns_halo, None, device=dev)
+    ms = timeit(lambda: kernels.agg_packed_sum_rows(v_halo, meta, out_rows, halo, rs, out, accumulate=True))
+    print(f"halo pass: hub threshold {t:5d} ({nh} hub rows): {ms:.4f} ms", flush=True)
+for t in (64, 128, 256, 512, 1024):
+    v_own, nh = mkview_hub(oro, ocols, nr, t)
+    meta = kernels.pack_edge_meta(v_own, ns_own, None, device=dev)
+    ms = timeit(lambda: kernels.agg_packed_sum_rows(v_own, meta, None, x_own, rs, out, accumulate=False))
+    print(f"own pass : hub threshold {t:5d} ({nh} hub rows): {ms:.4f} ms", flush=True)

@@ -16,11 +16,17 @@ GATConv gives ``dV0 = dV1`` once; ``x*x`` would give ``g*x``, not ``2*g*x``).
 """
 from __future__ import annotations
 
+import os
+
 from .passes import DCE, fuse, optimize, resolve
+from .passes.peephole import factor_aggregations
 from .program import Program, Stmt, Var
 from .registry import GradCtx, look_up_registry
 from .schema import Schema
 from .utils import is_const_scalar
+
+#: STG_PEEPHOLE=0 keeps inner aggregations as separate units (A/B runs, tests of the unfactored program)
+PEEPHOLE = os.environ.get("STG_PEEPHOLE", "1") != "0"
 
 
 def diff(ids, forward_units, out_vars):
@@ -120,5 +126,22 @@ def diff(ids, forward_units, out_vars):
     DCE(bprog, list(grad_out.values()))
     replaced = optimize(bprog)
     grad_out = {x: resolve(g, replaced) for x, g in grad_out.items()}
+    if PEEPHOLE:
+        # inner aggregations that equal node-wise arithmetic on a forward aggregation the kernel stored (GAT: K2 is one
+        # unit again); a forward aggregation that is only NAMED by the rewrite becomes a stored ret of its unit
+        stored = set(materialised)
+        for s in fstmts:
+            if s.is_agg():
+                stored.add(s.ret)
+        rewritten = factor_aggregations(ids, bprog, fstmts, stored, list(grad_out.values()))
+        if rewritten:
+            for st in bprog:
+                for a in st.var_args():
+                    if a in produced and produced[a].is_agg() and a not in materialised:
+                        unit_of[a].add_ret_val(a)
+                        materialised.add(a)
+            DCE(bprog, list(grad_out.values()))
+            replaced = optimize(bprog)
+            grad_out = {x: resolve(g, replaced) for x, g in grad_out.items()}
     backward_units = fuse(bprog, list(grad_out.values()))
     return backward_units, grad_in, grad_out

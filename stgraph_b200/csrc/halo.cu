@@ -349,7 +349,7 @@ STG_API int stg_exchange_destroy(void* handle) {
 STG_API int stg_exchange_run_f32(void* handle, const float* own, int32_t feat, const int64_t* send_rows,
                                  const int64_t* send_off, float* send_buf, float* const* peer_dst,
                                  int32_t* const* peer_flags, const int32_t* seq_values, int32_t value, int32_t num_parts,
-                                 int32_t my_rank, void* stream) {
+                                 int32_t my_rank, int32_t per_peer_gathers, void* stream) {
   StgExchange* h = static_cast<StgExchange*>(handle);
   STG_CHECK_ARG(h != nullptr, "exchange handle is NULL");
   STG_CHECK_ARG(num_parts >= 1 && num_parts <= STG_MAX_PARTS, "num_parts must be in [1, %d]", STG_MAX_PARTS);
@@ -357,21 +357,26 @@ STG_API int stg_exchange_run_f32(void* handle, const float* own, int32_t feat, c
   STG_CHECK_ARG(send_off && peer_dst && peer_flags && seq_values, "NULL argument");
   STG_CHECK_ARG(value >= 0 && value < 65536, "sequence value must be in [0, 65536)");
   cudaStream_t s = as_stream(stream);
-  int used = 0;
+  if (!per_peer_gathers) {     // one kernel for all segments (it runs BESIDE a persistent grid: a second launch would starve)
+    int rc = stg_rows_gather_f32(own, feat, send_rows, send_off[num_parts], send_buf, 0, s);
+    if (rc != STG_OK) return rc;
+    STG_CUDA(cudaEventRecord(h->packed[0], s));
+  }
   for (int i = 1; i < num_parts; ++i) {
     const int q = (my_rank + i) % num_parts;
     const int64_t rows = send_off[q + 1] - send_off[q];
     STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
     cudaStream_t cs = h->copy[(i - 1) % h->n_streams];
-    used = std::max(used, (i - 1) % h->n_streams + 1);
-    if (rows > 0) {
-      STG_CHECK_ARG(own && send_rows && send_buf && peer_dst[q], "NULL buffer for a non-empty segment (peer %d)", q);
-      float* seg = send_buf + static_cast<size_t>(send_off[q]) * feat;
-      int rc = stg_rows_gather_f32(own, feat, send_rows + send_off[q], rows, seg, 0, s);
-      if (rc != STG_OK) return rc;
+    if (rows > 0) STG_CHECK_ARG(own && send_rows && send_buf && peer_dst[q], "NULL buffer for a non-empty segment (peer %d)", q);
+    if (per_peer_gathers) {
+      if (rows > 0) {
+        float* seg = send_buf + static_cast<size_t>(send_off[q]) * feat;
+        int rc = stg_rows_gather_f32(own, feat, send_rows + send_off[q], rows, seg, 0, s);
+        if (rc != STG_OK) return rc;
+      }
+      STG_CUDA(cudaEventRecord(h->packed[q], s));
     }
-    STG_CUDA(cudaEventRecord(h->packed[q], s));
-    STG_CUDA(cudaStreamWaitEvent(cs, h->packed[q], 0));
+    STG_CUDA(cudaStreamWaitEvent(cs, h->packed[per_peer_gathers ? q : 0], 0));
     if (rows > 0)
       STG_CUDA(cudaMemcpyAsync(peer_dst[q], send_buf + static_cast<size_t>(send_off[q]) * feat,
                                static_cast<size_t>(rows) * feat * sizeof(float), cudaMemcpyDeviceToDevice, cs));

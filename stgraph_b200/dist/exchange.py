@@ -108,6 +108,9 @@ class HaloExchange:
         t_own = int(plan.own_cols.numel()) * (self.feat / 100.0) / 25e9
         gf = os.environ.get("STG_GATHER_FIRST")
         self.gather_first = (t_x > 0.8 * t_own) if gf is None else gf == "1"
+        # one gather kernel for all peers (measured at 8 GPUs: seven per-peer kernels took 0.13 ms against 0.06-0.08 ms
+        # and their copies did not start any earlier); STG_PER_PEER_GATHERS=1 keeps the pipelined form for A/B runs
+        self.per_peer_gathers = 1 if (self.gather_first and os.environ.get("STG_PER_PEER_GATHERS", "0") == "1") else 0
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:
@@ -152,7 +155,7 @@ class HaloExchange:
                 side.wait_event(self._ev_in)
             _lib.call("stg_exchange_run_f32", self._handle, x_own.data_ptr(), self.feat, plan.send_index.data_ptr(),
                       self._send_off, self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(),
-                      it & 0xFFFF, world, rank, gs.cuda_stream)
+                      it & 0xFFFF, world, rank, self.per_peer_gathers, gs.cuda_stream)
             if ev:
                 ev[5].record(gs)
                 _lib.call("stg_exchange_join", self._handle, side.cuda_stream)
