@@ -88,20 +88,27 @@ class HaloPlan:
 
     # ------------------------------------------------------- overlapped two-pass form
     @staticmethod
-    def hub_threshold_for(n_edges: int) -> int:
+    def hub_threshold_for(n_edges: int, n_rows: int) -> int:
         """Rows longer than this go to the block-per-row kernel.  One warp walks a row at ~8 edges per memory round
         trip, so the longest warp-owned row bounds the launch from below: 1024 edges (~0.1 ms) are invisible in the
         2 ms pass over the whole graph but a third of a 0.3 ms pass over one rank's share of an 8-way partition, and
         more than the whole halo-source pass (ncu, r2: 23 % of the warp samples of that pass sat at the final barrier
-        behind one long row).  Scale the threshold with the work of the launch."""
-        per = int(os.environ.get("STG_HUB_EDGES_PER_UNIT", "30000"))      # A/B knob
-        return int(min(HUB_THRESHOLD, max(64, n_edges // max(per, 1))))
+        behind one long row).  Measured on rank 0's share of config 5: at P=8 the halo-source pass (3.5 edges per row)
+        takes 0.306 / 0.146 / 0.143 / 0.153 / 0.218 ms at no split / 64 / 128 / 256 / 1024 and the own-source pass 0.409 /
+        0.281 / 0.260 / 0.266 / 0.295 ms at 64 / 128 / 256 / 512 / 1024; at P=2 (29 M edges) 1.17 / 1.03 / 1.02 / 1.08 ms at
+        128 / 256 / 512 / 1024."""
+        env = os.environ.get("STG_PART_HUB_THRESHOLD")       # A/B knob
+        if env:
+            return int(env)
+        if n_rows > 0 and n_edges < 8 * n_rows:
+            return 128
+        return 256 if n_edges < 16_000_000 else 512
 
     def _make_view(self, ro, cols, eids, n_rows=None):
         dev = ro.device
         n_rows = self.n_rows if n_rows is None else n_rows
         n_e = int(cols.shape[0])
-        threshold = self.hub_threshold_for(n_e)
+        threshold = self.hub_threshold_for(n_e, n_rows)
         cap = n_e // max(threshold, 1) + 1
         hub_rows = torch.empty(cap, dtype=torch.int32, device=dev)
         hub_count = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -75,3 +75,96 @@ def _covid_check(ec):
 def test_england_covid_loader():
     for kw in ({}, {"cutoff_time": 30}, {"lags": 12}, {"redownload": True}):
         _covid_check(EnglandCovidDataLoader(**kw))
+
+
+# ---- the remaining static-temporal loaders (reference: tests/dataset/temporal/test_*DataLoader.py) -----------------
+def _lag_errors(cls):
+    for bad, exc, msg in (("lags", TypeError, "lags must be of type int"), (-1, ValueError, "lags must be a positive integer")):
+        with pytest.raises(exc) as e:
+            cls(lags=bad)
+        assert str(e.value) == msg
+    for bad, exc, msg in (("time", TypeError, "cutoff_time must be of type int"),
+                          (-1, ValueError, "cutoff_time must be a positive integer")):
+        with pytest.raises(exc) as e:
+            cls(cutoff_time=bad)
+        assert str(e.value) == msg
+
+
+def test_hungarycp_loader_shapes_and_errors():
+    from stgraph_b200.dataset import HungaryCPDataLoader
+
+    for kw in ({"verbose": True}, {"lags": 6}, {"cutoff_time": 100}, {"redownload": True}):
+        h = HungaryCPDataLoader(**kw)
+        assert h.gdata["total_timestamps"] == (521 if not h._cutoff_time else h._cutoff_time)
+        assert h.gdata["num_nodes"] == 20 and h.gdata["num_edges"] == 102
+        assert len(h.get_edges()) == 102 and len(h.get_edges()[0]) == 2 and len(h.get_edge_weights()) == 102
+        assert len(h.get_all_targets()) == h.gdata["total_timestamps"] - h._lags
+        assert h.get_all_targets()[0].shape == (20,)
+    _lag_errors(HungaryCPDataLoader)
+
+
+def test_pedalme_loader_shapes_and_errors():
+    from stgraph_b200.dataset import PedalMeDataLoader
+
+    for kw in ({"verbose": True}, {"redownload": True}, {"lags": 6}, {"cutoff_time": 20}):
+        p = PedalMeDataLoader(**kw)
+        assert p.gdata["total_timestamps"] == (36 if not p._cutoff_time else p._cutoff_time)
+        assert p.gdata["num_nodes"] == 15 and p.gdata["num_edges"] == 225
+        assert len(p.get_edges()) == 225 and all(len(e) == 2 for e in p.get_edges()) and len(p.get_edge_weights()) == 225
+        assert p.get_all_targets().shape == (p.gdata["total_timestamps"] - p._lags, 15)
+    _lag_errors(PedalMeDataLoader)
+
+
+def test_windmill_loader_sizes_and_errors():
+    from stgraph_b200.dataset import WindmillOutputDataLoader
+
+    for size, (n, e) in {"large": (319, 101761), "medium": (26, 676), "small": (11, 121)}.items():
+        for kw in ({"verbose": True}, {"lags": 4}, {"cutoff_time": 100}):
+            w = WindmillOutputDataLoader(size=size, **kw)
+            assert w.gdata["total_timestamps"] == (17472 if not w._cutoff_time else w._cutoff_time)
+            assert w.gdata["num_nodes"] == n and w.gdata["num_edges"] == e
+            assert len(w.get_edges()) == e and len(w.get_edge_weights()) == e
+            assert len(w.get_all_targets()) == w.gdata["total_timestamps"] and w.get_all_targets()[0].shape == (n,)
+    with pytest.raises(TypeError) as ex:
+        WindmillOutputDataLoader(size=1)
+    assert str(ex.value) == "size must be of type string"
+    with pytest.raises(ValueError):
+        WindmillOutputDataLoader(size="tiny")
+    _lag_errors(WindmillOutputDataLoader)
+
+
+def test_montevideobus_loader_shapes_and_errors():
+    from stgraph_b200.dataset import MontevideoBusDataLoader
+
+    for kw in ({"verbose": True}, {"redownload": True}, {"lags": 6}, {"cutoff_time": 50}):
+        m = MontevideoBusDataLoader(**kw)
+        t = m.gdata["total_timestamps"]
+        assert t == (744 if not m._cutoff_time else m._cutoff_time)
+        assert m.gdata["num_nodes"] == 675 and m.gdata["num_edges"] == 690
+        assert len(m.get_edges()) == 690 and len(m.get_edge_weights()) == 690
+        assert m.get_all_features().shape == (t - m._lags, 675, m._lags)
+        assert m.get_all_targets().shape == (t - m._lags, 675)
+        # the feature window of sample i ends right before its target
+        assert np.allclose(m.get_all_features()[1][:, -1], m.get_all_targets()[0])
+    _lag_errors(MontevideoBusDataLoader)
+
+
+def test_metrla_loader_shapes_and_errors():
+    from stgraph_b200.dataset import METRLADataLoader
+
+    for kw in ({"verbose": True}, {"redownload": True}, {"num_timesteps_in": 8, "num_timesteps_out": 8}, {"cutoff_time": 50}):
+        r = METRLADataLoader(**kw)
+        t = r.gdata["total_timestamps"]
+        assert t == (100 if not r._cutoff_time else r._cutoff_time)
+        assert r.gdata["num_nodes"] == 207 and r.gdata["num_edges"] == 1722
+        assert len(r.get_edges()) == 1722 and len(r.get_edges()[0]) == 2 and len(r.get_edge_weights()) == 1722
+        k = t - (r._num_timesteps_in + r._num_timesteps_out) + 1
+        assert r.get_all_features().shape == (k, 207, 2, r._num_timesteps_in)
+        assert r.get_all_targets().shape == (k, 207, r._num_timesteps_out)
+    for name in ("num_timesteps_in", "num_timesteps_out"):
+        with pytest.raises(TypeError) as ex:
+            METRLADataLoader(**{name: name})
+        assert str(ex.value) == f"{name} must be of type int"
+        with pytest.raises(ValueError) as ex:
+            METRLADataLoader(**{name: -1})
+        assert str(ex.value) == f"{name} must be a positive integer"

@@ -474,9 +474,12 @@ def test_state_stack_does_not_grow_without_a_backward(cuda):
         for _ in range(5):
             layer(g, x)
     ctx = next(iter(layer.stgraph._ctx_map.values()))
-    stack = ctx._executor_cache.ts.tensor_map_stack
-    assert len(stack) == 0
+    assert len(ctx._executor_cache.ts.tensor_map_stack) == 0
     y = layer(g, x)                       # weights need a gradient: one entry, popped by backward
+    stack = ctx._executor_cache.ts.tensor_map_stack      # (executors are keyed by the inputs' requires_grad signature)
+    assert len(stack) == 1
+    with torch.no_grad():
+        layer(g, x @ layer.weight.detach() * 0 + x)      # a no-grad call in between leaves the pending entry alone
     assert len(stack) == 1
     y.sum().backward()
     assert len(stack) == 0
