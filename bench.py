@@ -472,6 +472,60 @@ def main():
                              "api": "per rank: pinned host rows -> device, PartitionedGraph.aggregate fwd + bwd, results -> "
                                     "pinned host; device time, max over ranks; bytes summed over ranks"}
 
+    # ---- 2-layer GCN 100 -> 100 -> 47 training epoch on the same graph through the layer API (GCNConv on a StaticGraph /
+    # on a PartitionedGraph; fwd + bwd + gradient all-reduce + Adam), the whole-model figure SURVEY.md section 8(e) asks
+    # to report beside the aggregation-only scaling
+    if not args.no_extras:
+        try:
+            from stgraph_b200.dist import all_reduce_gradients
+            from stgraph_b200.nn.pytorch import GCNConv
+
+            torch.manual_seed(7)
+            l1, l2 = GCNConv(FEAT, 100, activation=torch.relu).to(dev), GCNConv(100, 47).to(dev)
+            params = list(l1.parameters()) + list(l2.parameters())
+            if world > 1:
+                for p_ in params:
+                    dist.broadcast(p_.data, 0)
+                gg, xin = pg, x_own
+                pg.set_ndata("norm", nl.reshape(-1, 1))
+            else:
+                gg, xin = graph, x
+                graph.set_ndata("norm", norm.reshape(-1, 1))
+            labels = torch.randint(0, 47, (xin.shape[0],), device=dev)
+            opt = torch.optim.Adam(params, lr=1e-2)
+
+            def epoch():
+                opt.zero_grad()
+                loss = torch.nn.functional.cross_entropy(l2(gg, l1(gg, xin)), labels, reduction="sum") / n
+                loss.backward()
+                if world > 1:
+                    all_reduce_gradients(params)
+                opt.step()
+                return loss
+
+            for _ in range(2):
+                epoch()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                loss = epoch()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / 3, float(loss)], device=dev)
+            if world > 1:
+                tm = t.clone()
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                t[0] = tm[0]
+            extras["gcn_2layer_epoch"] = {"ms_per_epoch": float(t[0]), "loss": float(t[1]),
+                                          "model": "GCNConv(100,100,relu) -> GCNConv(100,47), cross-entropy on random labels, Adam",
+                                          "api": "stgraph_b200.nn.pytorch.GCNConv on " + ("PartitionedGraph (local rows; weight "
+                                                 "gradients all-reduced)" if world > 1 else "StaticGraph")}
+            del l1, l2, opt, params
+        except Exception as ex:
+            extras["gcn_2layer_epoch"] = {"error": repr(ex)[:300]}
+
     if rank == 0 and world == 1 and not args.no_extras:
         # ---- the plain kernel (column load + dependent norm gather per edge) on the same inputs, for the record ----
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -193,8 +193,10 @@ int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t* send_ro
  *                          releases "copy rows to peer_dst[q], then 4-byte flag to peer_flags[q]" on one of the
  *                          handle's copy streams.  When the call returns, `stream` holds only the gathers: launch the
  *                          aggregation pass behind them so that they do not queue behind a persistent grid.
- *                          per_peer_gathers == 0: ONE gather kernel for all segments (for a `stream` that runs beside
- *                          the aggregation pass), every copy released by its completion;
+ *                          per_peer_gathers = number of gather launches the P-1 segments are packed by (<= 1: ONE
+ *                          kernel for all segments -- for a `stream` that runs beside the aggregation pass --, every
+ *                          copy released by its completion; k: the copies of the first (P-1)/k peers start after 1/k
+ *                          of the packing);
  *   stg_exchange_join    : make a stream wait for all copies of the last run (before send_buf is refilled). */
 int stg_exchange_create(int32_t n_streams, void** handle);
 int stg_exchange_destroy(void* handle);

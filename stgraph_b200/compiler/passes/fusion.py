@@ -23,6 +23,10 @@ from ..utils import ValType, is_const_scalar
 def _is_torch_only(stmt) -> bool:
     if stmt.is_agg():
         return False
+    if getattr(stmt, "hoist", False) and stmt.is_nodewise():
+        # node-wise arithmetic on stored tensors that a pass asked to run ONCE PER NODE before the kernel (peephole.py):
+        # inside a kernel that walks the other side's rows it would be re-evaluated, operands gathered, for every edge
+        return True
     if stmt.callback is not None and stmt.op_name.lower() in ("sum", "view"):
         return True
     return not is_vm_supported(stmt)

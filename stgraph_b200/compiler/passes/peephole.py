@@ -7,8 +7,11 @@ gradient of ``out[v] = sum_e w(e) * X[u]`` with respect to something inside ``w`
 
 which starts a second kernel because a unit holds one aggregation stage.  Since ``c`` and ``g`` do not depend on the
 edge, ``A[v] = c(v) * <g[v], sum_e w(e) X[u]> = c(v) * <g[v], out[v]>``: node-wise arithmetic on a tensor the forward
-kernel stored anyway.  After the rewrite stock GATConv's backward is ONE unit (three output aggregations) instead of
-two, i.e. two launches (source-parallel + destination-parallel) instead of four.
+kernel stored anyway.  After the rewrite stock GATConv's backward is ONE compiled unit (three output aggregations)
+instead of two, i.e. two launches (source-parallel + destination-parallel) instead of four; the node-wise arithmetic
+itself is marked for hoisting and runs once per node as a torch unit in front of the kernel (evaluated inside the
+source-parallel launch it would be redone, with three 512-byte gathers, for every edge: measured 15.6 ms against
+12.7 ms for the unfactored program on config 3).
 
 How (own design; the reference runs sympy over the whole program and accepts any textual shortening): every value is
 tracked as a monomial ``coef * prod(var ** exp)`` over the variables the backward kernel reads from memory, through
@@ -129,6 +132,7 @@ def factor_aggregations(ids, bprog, forward_stmts, stored, outputs):
                     continue                      # shapes disagree: leave the aggregation alone
                 for s2 in new:
                     s2.ret._requires_grad = False
+                    s2.hoist = True               # node-wise on stored tensors: run once per node (fusion.py)
                 idx = bprog.stmts.index(st)
                 bprog.stmts[idx:idx + 1] = new
                 bprog.replace_uses(st.ret, cur)

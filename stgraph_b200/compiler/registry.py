@@ -204,7 +204,8 @@ _TABLE = [
     OpDef("aggmax", OP_ACC_MAX, None, _aggmax_grad, is_agg=True, acc_init=float("-inf")),
     OpDef("aggmin", OP_ACC_MIN, None, _no_grad("AggMin"), is_agg=True, acc_init=float("inf")),
     OpDef("aggmean", OP_ACC_SUM, None, _no_grad("AggMean"), is_agg=True, acc_init=0.0),
-    OpDef("sum", OP_GSUM, None, _no_grad("Sum")),
+    OpDef("sum", OP_GSUM, lambda x, dim=-1, keep_dim=True, **_: x.sum(dim=(dim % (x.dim() - 1)) + 1, keepdim=keep_dim),
+          _no_grad("Sum")),
     OpDef("gtypecast", None, None, _no_grad("GTypeCast")),
 ]
 

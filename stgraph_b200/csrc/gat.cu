@@ -24,6 +24,8 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace stg {
@@ -62,6 +64,7 @@ struct GatParams {
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ hub_count;
   int hub_threshold, hub_capacity;
+  int* queue;            // global row queue of the view (StgCsrView::work_queue) or NULL
   int num_rows;
   int heads, dim, hd;        // hd = heads*dim
   int lph;                   // lanes per head inside a chunk (dim / VEC), power of two
@@ -560,21 +563,49 @@ __global__ void __cluster_dims__(kGatCluster, 1, 1) __launch_bounds__(HubThreads
 // KIND: 0 forward, 1 backward pass A (destination-parallel), 2 backward pass B (source-parallel).
 constexpr int kGatRowsPerWarp = 16;
 
-template <int VEC, int NACC, int KIND>
+// GQ: global row queue as in agg.cu (persistent grid, warps draw chunks of rows_per_block rows from the view's device
+// counter; the last block rearms it): config 3 has 1323 blocks of 128 rows on 592 block slots, i.e. 2.2 waves whose
+// last one is a third full -- with the queue every warp stays busy until the rows run out.
+template <int VEC, int NACC, int KIND, bool GQ = false>
 __global__ void __launch_bounds__(kGatThreads, NACC == 1 ? 4 : 1) gat_rows_pipe_kernel(const GatParams p, int rows_per_block) {
   constexpr int GROUP = 32;
   __shared__ int next_row;
   Lanes<VEC, GROUP, NACC> L;
   L.init(p);
   const int lane = threadIdx.x & 31;
-  const int first = blockIdx.x * rows_per_block;
-  const int last = min(first + rows_per_block, p.num_rows);
-  if (threadIdx.x == 0) next_row = first;
-  __syncthreads();
+  const int first = GQ ? 0 : blockIdx.x * rows_per_block;
+  const int last = GQ ? p.num_rows : min(first + rows_per_block, p.num_rows);
+  int q_cur = 0, q_pos = rows_per_block, q_nxt = 0;
+  if constexpr (GQ) {
+    if (lane == 0) q_nxt = atomicAdd(p.queue, 1);
+  } else {
+    if (threadIdx.x == 0) next_row = first;
+    __syncthreads();
+  }
   auto draw = [&]() {
-    int r = 0;
-    if (lane == 0) r = atomicAdd(&next_row, 1);
-    return __shfl_sync(0xffffffffu, r, 0);
+    if constexpr (GQ) {
+      if (q_pos == rows_per_block && q_cur < p.num_rows) {
+        q_cur = __shfl_sync(0xffffffffu, q_nxt, 0) * rows_per_block;
+        q_pos = 0;
+        if (lane == 0 && q_cur < p.num_rows) q_nxt = atomicAdd(p.queue, 1);
+      }
+      return q_cur + q_pos++;
+    } else {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&next_row, 1);
+      return __shfl_sync(0xffffffffu, r, 0);
+    }
+  };
+  auto finish = [&]() {
+    if constexpr (GQ) {
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(p.queue + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        p.queue[0] = 0;
+        p.queue[1] = 0;
+        __threadfence();
+      }
+    }
+    grid_dependency_wait();
   };
   auto offsets = [&](int row, int& beg, int& end) {      // end = -1: nothing to do (past the end)
     beg = 0;
@@ -589,7 +620,7 @@ __global__ void __launch_bounds__(kGatThreads, NACC == 1 ? 4 : 1) gat_rows_pipe_
   };
   int row0 = draw();
   if (row0 >= last) {
-    grid_dependency_wait();
+    finish();
     return;
   }
   int beg0, end0, beg1, end1;
@@ -620,7 +651,17 @@ __global__ void __launch_bounds__(kGatThreads, NACC == 1 ? 4 : 1) gat_rows_pipe_
     row0 = row1; beg0 = beg1; end0 = end1; c0 = c1;
     row1 = row2; beg1 = beg2; end1 = end2;
   }
-  grid_dependency_wait();
+  finish();
+}
+
+// Rows a warp draws from the global queue at a time (STG_GAT_CHUNK; 0 = static block ranges; read once).
+inline int gat_queue_chunk() {
+  static const int v = [] {
+    const char* e = getenv("STG_GAT_CHUNK");
+    const int c = e ? atoi(e) : 4;
+    return c < 0 ? 0 : (c > 1024 ? 1024 : c);
+  }();
+  return v;
 }
 
 template <int VEC, int GROUP, int NACC>
@@ -640,6 +681,15 @@ int launch_gat(const GatParams& p, int which, cudaStream_t s) {
   }
   if constexpr (GROUP == 32) {
     if (p.num_rows >= 4096) {      // the queue pays off once there are several blocks per SM
+      if (p.queue != nullptr && gat_queue_chunk() > 0) {
+        const int gblocks = std::min(sm_count() * (NACC == 1 ? 4 : 1), (p.num_rows + 7) / 8);
+        const int ch = gat_queue_chunk();
+        if (which == 0) STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 0, true>, gblocks, kGatThreads, s, hubs, p, ch));
+        else if (which == 1) STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 1, true>, gblocks, kGatThreads, s, hubs, p, ch));
+        else STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 2, true>, gblocks, kGatThreads, s, hubs, p, ch));
+        STG_LAUNCH_CHECK("gat rows (global queue) kernel");
+        return STG_OK;
+      }
       const int rpb = (kGatThreads / 32) * kGatRowsPerWarp;
       const int pblocks = (p.num_rows + rpb - 1) / rpb;
       if (which == 0) STG_CUDA(launch_overlapped(gat_rows_pipe_kernel<VEC, NACC, 0>, pblocks, kGatThreads, s, hubs, p, rpb));
@@ -691,6 +741,7 @@ int check_view(const StgCsrView* g) {
 void bind_view(GatParams& p, const StgCsrView* g) {
   p.row_off = g->row_offset;
   p.col = g->column_indices;
+  p.queue = g->work_queue;
   const bool hubs = g->hub_rows && g->hub_count && g->hub_threshold > 0;
   p.hub_rows = hubs ? g->hub_rows : nullptr;
   p.hub_count = hubs ? g->hub_count : nullptr;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kGateThreads) clamp_bwd_kernel(const float* __
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = y[i];
-    d_a[i] = ((v > lo && v < hi) || v != v) ? d_y[i] : 0.f;      // a NaN value passes its gradient on (torch.clamp)
+    d_a[i] = (v > lo && v < hi) ? d_y[i] : 0.f;      // a NaN value gets no gradient, like torch.clamp's mask
   }
 }
 

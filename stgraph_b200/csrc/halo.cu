@@ -357,31 +357,49 @@ STG_API int stg_exchange_run_f32(void* handle, const float* own, int32_t feat, c
   STG_CHECK_ARG(send_off && peer_dst && peer_flags && seq_values, "NULL argument");
   STG_CHECK_ARG(value >= 0 && value < 65536, "sequence value must be in [0, 65536)");
   cudaStream_t s = as_stream(stream);
-  if (!per_peer_gathers) {     // one kernel for all segments (it runs BESIDE a persistent grid: a second launch would starve)
-    int rc = stg_rows_gather_f32(own, feat, send_rows, send_off[num_parts], send_buf, 0, s);
-    if (rc != STG_OK) return rc;
-    STG_CUDA(cudaEventRecord(h->packed[0], s));
-  }
-  for (int i = 1; i < num_parts; ++i) {
-    const int q = (my_rank + i) % num_parts;
-    const int64_t rows = send_off[q + 1] - send_off[q];
-    STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
-    cudaStream_t cs = h->copy[(i - 1) % h->n_streams];
-    if (rows > 0) STG_CHECK_ARG(own && send_rows && send_buf && peer_dst[q], "NULL buffer for a non-empty segment (peer %d)", q);
-    if (per_peer_gathers) {
-      if (rows > 0) {
-        float* seg = send_buf + static_cast<size_t>(send_off[q]) * feat;
-        int rc = stg_rows_gather_f32(own, feat, send_rows + send_off[q], rows, seg, 0, s);
-        if (rc != STG_OK) return rc;
+  // The peers are served in send order q = rank+1, rank+2, ...; their segments are packed by `groups` gather kernels
+  // (1: one kernel for everything -- the only choice when `stream` runs beside a persistent grid, where a second
+  // launch would starve; P-1: one kernel per peer; in between: the first copies start after 1/groups of the packing).
+  const int peers = num_parts - 1;
+  int groups = per_peer_gathers <= 0 ? 1 : (per_peer_gathers > peers ? peers : per_peer_gathers);
+  if (groups < 1) groups = 1;
+  int done_peers = 0;
+  for (int gi = 0; gi < groups; ++gi) {
+    const int upto = static_cast<int>((static_cast<int64_t>(peers) * (gi + 1)) / groups);
+    // segments of consecutive send-order peers are not contiguous in send_buf (it is ordered by rank): one launch each,
+    // unless the whole buffer is packed at once
+    if (groups == 1) {
+      int rc = stg_rows_gather_f32(own, feat, send_rows, send_off[num_parts], send_buf, 0, s);
+      if (rc != STG_OK) return rc;
+    } else {
+      for (int i = done_peers + 1; i <= upto; ++i) {
+        const int q = (my_rank + i) % num_parts;
+        const int64_t rows = send_off[q + 1] - send_off[q];
+        STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
+        if (rows > 0) {
+          STG_CHECK_ARG(own && send_rows && send_buf, "NULL buffer for a non-empty segment (peer %d)", q);
+          int rc = stg_rows_gather_f32(own, feat, send_rows + send_off[q], rows,
+                                       send_buf + static_cast<size_t>(send_off[q]) * feat, 0, s);
+          if (rc != STG_OK) return rc;
+        }
       }
-      STG_CUDA(cudaEventRecord(h->packed[q], s));
     }
-    STG_CUDA(cudaStreamWaitEvent(cs, h->packed[per_peer_gathers ? q : 0], 0));
-    if (rows > 0)
-      STG_CUDA(cudaMemcpyAsync(peer_dst[q], send_buf + static_cast<size_t>(send_off[q]) * feat,
-                               static_cast<size_t>(rows) * feat * sizeof(float), cudaMemcpyDeviceToDevice, cs));
-    if (peer_flags[q] != nullptr)
-      STG_CUDA(cudaMemcpyAsync(peer_flags[q], seq_values + value, sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
+    STG_CUDA(cudaEventRecord(h->packed[gi], s));
+    for (int i = done_peers + 1; i <= upto; ++i) {
+      const int q = (my_rank + i) % num_parts;
+      const int64_t rows = send_off[q + 1] - send_off[q];
+      STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
+      cudaStream_t cs = h->copy[(i - 1) % h->n_streams];
+      STG_CUDA(cudaStreamWaitEvent(cs, h->packed[gi], 0));
+      if (rows > 0) {
+        STG_CHECK_ARG(send_buf && peer_dst[q], "NULL buffer for a non-empty segment (peer %d)", q);
+        STG_CUDA(cudaMemcpyAsync(peer_dst[q], send_buf + static_cast<size_t>(send_off[q]) * feat,
+                                 static_cast<size_t>(rows) * feat * sizeof(float), cudaMemcpyDeviceToDevice, cs));
+      }
+      if (peer_flags[q] != nullptr)
+        STG_CUDA(cudaMemcpyAsync(peer_flags[q], seq_values + value, sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
+    }
+    done_peers = upto;
   }
   return STG_OK;
 }

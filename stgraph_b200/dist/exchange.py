@@ -108,9 +108,9 @@ class HaloExchange:
         t_own = int(plan.own_cols.numel()) * (self.feat / 100.0) / 25e9
         gf = os.environ.get("STG_GATHER_FIRST")
         self.gather_first = (t_x > 0.8 * t_own) if gf is None else gf == "1"
-        # one gather kernel for all peers (measured at 8 GPUs: seven per-peer kernels took 0.13 ms against 0.06-0.08 ms
-        # and their copies did not start any earlier); STG_PER_PEER_GATHERS=1 keeps the pipelined form for A/B runs
-        self.per_peer_gathers = 1 if (self.gather_first and os.environ.get("STG_PER_PEER_GATHERS", "0") == "1") else 0
+        # number of gather launches (measured at 8 GPUs: seven per-peer kernels take 0.13 ms, twice one kernel's time,
+        # and buy nothing; two groups let the first copies start after half of the packing)
+        self.per_peer_gathers = int(os.environ.get("STG_GATHER_GROUPS", "2")) if self.gather_first else 1
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:

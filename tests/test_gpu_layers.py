@@ -496,4 +496,4 @@ def test_fused_clamp_propagates_nan_like_torch(cuda):
     got.backward(torch.ones_like(got))
     a3 = a.clone().requires_grad_(True)
     torch.clamp(a3 * 1.0, -1e6, 1e6).backward(torch.ones_like(a3))
-    assert torch.equal(a2.grad, a3.grad)
+    assert torch.equal(a2.grad, a3.grad)            # torch's mask: no gradient where the value is NaN or clamped
