@@ -20,6 +20,8 @@ from .. import _lib
 from . import registry as R
 from .utils import ValType, is_const_scalar, numel
 
+#: STG_SHARE_EDGE=0: every launch of a unit recomputes the edge values it aggregates (A/B)
+SHARE_EDGE_VALUES = __import__("os").environ.get("STG_SHARE_EDGE", "1") != "0"
 PRE, LOOP, POST = 0, 1, 2
 SIDE_CENTER, SIDE_NBR, SIDE_EDGE, SIDE_PARAM = 0, 1, 2, 3
 
@@ -52,14 +54,15 @@ def _shape2(shape):
     return [1] * (2 - len(s)) + s
 
 
-def _slice(unit, targets):
-    """Statements of the unit needed to compute ``targets`` (in program order)."""
+def _slice(unit, targets, stop=()):
+    """Statements of the unit needed to compute ``targets`` (in program order); ``stop``: Vars another launch has
+    already stored (read from memory instead of being recomputed), unless they are targets themselves."""
     produced = {s.ret: s for s in unit.program}
     need, stack = set(), list(targets)
     while stack:
         v = stack.pop()
         st = produced.get(v)
-        if st is None or st in need:
+        if st is None or st in need or (v in stop and v not in targets):
             continue
         need.add(st)
         stack.extend(st.var_args())
@@ -261,9 +264,18 @@ class _VmBuilder:
             expire.setdefault(u, []).append(r)
         for i, ins in enumerate(seq):
             op, ph, dst, a, b, imm = ins
-            rd = reads(ins)
-            na = mapping[a] if a in rd and a in mapping else a
-            nb = mapping[b] if b in rd and b in mapping else b
+            # which OPERAND SLOTS hold registers (STORE's `a` and LOAD's `a` are tensor indices, ACC_*'s `dst` / ACC_READ's
+            # `a` accumulator indices): a tensor index that happens to equal a live register number must not be renamed
+            if op in (R.OP_LOAD, R.OP_CONST, R.OP_ACC_READ):
+                a_is_reg = b_is_reg = False
+            elif op == R.OP_STORE:
+                a_is_reg, b_is_reg = False, True
+            elif op in (R.OP_ADD, R.OP_SUB, R.OP_MUL, R.OP_DIV, R.OP_RELU_BWD, R.OP_AMAX_BWD):
+                a_is_reg = b_is_reg = True
+            else:                                     # ACC_*, unary ops, GSUM: `a` only
+                a_is_reg, b_is_reg = True, False
+            na = mapping[a] if a_is_reg and a in mapping else a
+            nb = mapping[b] if b_is_reg and b in mapping else b
             for r in expire.get(i, []):               # operands read here die here: their slot can hold the result
                 if r in mapping and first_def.get(r, -1) < i:
                     free.append(mapping[r])
@@ -386,8 +398,28 @@ def _lower_vm(unit, center, targets, stmts):
 def lower_unit(unit):
     """Return the launches (in execution order) that evaluate a compiled unit."""
     launches = []
-    for center, targets in plan_unit(unit):
-        stmts = _slice(unit, targets)
+    sides = plan_unit(unit)
+    stop = set()
+    if len(sides) == 2 and SHARE_EDGE_VALUES:
+        # An edge value that feeds aggregations on BOTH sides (GAT backward: the score gradient goes to d_el on the source
+        # side and to d_er on the destination side) is computed and stored by the first launch and loaded by the
+        # second, instead of re-evaluating its whole dependency chain (here a [H,D]-wide product + lane sum) per edge
+        # in both launches.
+        first = {st.ret for st in _slice(unit, sides[0][1])}
+        second_targets = set(sides[1][1])
+        shared = []
+        for st in unit.program:
+            if st.is_agg() and st.ret in second_targets:
+                p = st.args[0]
+                if not is_const_scalar(p) and p.is_edgevar() and p in first and p not in shared:
+                    shared.append(p)
+        for p in shared:
+            unit.add_ret_val(p)
+        if shared:
+            sides[0] = (sides[0][0], sides[0][1] + [p for p in shared if p not in sides[0][1]])
+            stop = set(shared)
+    for i, (center, targets) in enumerate(sides):
+        stmts = _slice(unit, targets, stop if i == 1 else ())
         la = _match_scaled_sum(unit, center, targets, stmts)
         if la is None:
             la = _lower_vm(unit, center, targets, stmts)
