@@ -188,22 +188,6 @@ int stg_halo_send_f32(const float* send_buf, int32_t feat, int32_t num_parts, in
 int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t* send_rows, const int64_t* send_off,
                           float* send_buf, float* const* peer_dst, int32_t* const* peer_flags, const int32_t* seq_values,
                           int32_t value, int32_t num_parts, int32_t my_rank, int32_t gather_blocks, void* stream);
-/* Pipelined form with private copy streams (a handle owns n_streams copy streams and the events between them):
- *   stg_exchange_run_f32 : for every peer q (in send order) a gather kernel packs q's rows on `stream`, an event
- *                          releases "copy rows to peer_dst[q], then 4-byte flag to peer_flags[q]" on one of the
- *                          handle's copy streams.  When the call returns, `stream` holds only the gathers: launch the
- *                          aggregation pass behind them so that they do not queue behind a persistent grid.
- *                          per_peer_gathers = number of gather launches the P-1 segments are packed by (<= 1: ONE
- *                          kernel for all segments -- for a `stream` that runs beside the aggregation pass --, every
- *                          copy released by its completion; k: the copies of the first (P-1)/k peers start after 1/k
- *                          of the packing);
- *   stg_exchange_join    : make a stream wait for all copies of the last run (before send_buf is refilled). */
-int stg_exchange_create(int32_t n_streams, void** handle);
-int stg_exchange_destroy(void* handle);
-int stg_exchange_run_f32(void* handle, const float* own, int32_t feat, const int64_t* send_rows, const int64_t* send_off,
-                         float* send_buf, float* const* peer_dst, int32_t* const* peer_flags, const int32_t* seq_values,
-                         int32_t value, int32_t num_parts, int32_t my_rank, int32_t per_peer_gathers, void* stream);
-int stg_exchange_join(void* handle, void* stream);
 int stg_peer_signal(int32_t* const* peer_flags, int32_t num_parts, int32_t my_rank, int32_t value, void* stream);
 int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, int64_t timeout_cycles,
                   int32_t* status, void* stream);

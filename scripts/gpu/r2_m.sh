@@ -1,0 +1,18 @@
+set -x
+mkdir -p gpurun_out
+run() { # name nproc env...
+  name=$1; np=$2; shift 2
+  env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $np --steps 20 --warmup 5 > gpurun_out/r2m_$name.log 2> gpurun_out/r2m_$name.err; echo "$name rc=$?"; tail -2 gpurun_out/r2m_$name.err | cut -c1-300
+  python - <<PY
+import json
+try:
+    l=json.loads(open('gpurun_out/r2m_$name.log').read().strip().splitlines()[-1])
+    print('$name', 'ms/step', round(l['ms_per_step'],4), 'value', round(l['value'],1), 'fwd_ms', round(l['roofline']['kernel_ms'],4), 'frac', round(l['roofline']['frac'],4))
+    print('  e2e', l.get('e2e'))
+    print('  gcn', l.get('gcn_2layer_epoch'))
+    for s in l['segments'][:3]: print(' ', s['rank'], s['fwd'])
+except Exception as ex: print('parse fail', ex)
+PY
+}
+run n8 8 A=1
+run n4 4 A=1

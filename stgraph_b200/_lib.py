@@ -103,11 +103,6 @@ _SIGNATURES = {
     "stg_halo_send_f32": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, _P(c_int64), _P(c_void_p), c_void_p], True),
     "stg_halo_exchange_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, _P(c_int64), c_void_p, _P(c_void_p), _P(c_void_p),
                                               c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p], True),
-    "stg_exchange_create": (ctypes.c_int, [c_int32, _P(c_void_p)], True),
-    "stg_exchange_destroy": (ctypes.c_int, [c_void_p], True),
-    "stg_exchange_run_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, _P(c_int64), c_void_p, _P(c_void_p),
-                                             _P(c_void_p), c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p], True),
-    "stg_exchange_join": (ctypes.c_int, [c_void_p, c_void_p], True),
     "stg_peer_signal": (ctypes.c_int, [_P(c_void_p), c_int32, c_int32, c_int32, c_void_p], True),
     "stg_peer_wait": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,

@@ -301,116 +301,3 @@ STG_API int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t*
   }
   return STG_OK;
 }
-
-// ---- pipelined exchange: per-peer gather kernels feed copy-engine copies on a few private streams ----------
-// Measured at 8 GPUs (r2): one gather kernel + seven back-to-back copies on one stream took 0.12 + 0.33 ms (every
-// copy pays ~10 us of start-up, and the gather shared the SMs with the aggregation pass it ran beside).  Here the
-// rows for peer q are gathered by their own small kernel (in send order), an event releases copy q on one of
-// `n_streams` private copy streams as soon as its segment is packed, and the 4-byte arrival flag for q follows its
-// data on the same stream, so a peer learns about its rows the moment they have landed.  The caller launches the
-// aggregation pass AFTER this call on its own stream: the gathers then own the chip for ~0.06 ms instead of
-// fighting a persistent grid for SM slots (a kernel launched behind that grid would wait for it to drain).
-struct StgExchange {
-  int n_streams;
-  cudaStream_t copy[8];
-  cudaEvent_t packed[STG_MAX_PARTS];
-  cudaEvent_t done[8];
-};
-
-STG_API int stg_exchange_create(int32_t n_streams, void** handle) {
-  STG_CHECK_ARG(handle != nullptr, "handle is NULL");
-  STG_CHECK_ARG(n_streams >= 1 && n_streams <= 8, "n_streams must be in [1, 8]");
-  StgExchange* h = new StgExchange();
-  h->n_streams = n_streams;
-  int lo = 0, hi = 0;
-  STG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  for (int i = 0; i < n_streams; ++i) {
-    STG_CUDA(cudaStreamCreateWithPriority(&h->copy[i], cudaStreamNonBlocking, hi));
-    STG_CUDA(cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
-  }
-  for (int q = 0; q < STG_MAX_PARTS; ++q) STG_CUDA(cudaEventCreateWithFlags(&h->packed[q], cudaEventDisableTiming));
-  *handle = h;
-  return STG_OK;
-}
-
-STG_API int stg_exchange_destroy(void* handle) {
-  StgExchange* h = static_cast<StgExchange*>(handle);
-  if (h == nullptr) return STG_OK;
-  for (int i = 0; i < h->n_streams; ++i) {
-    cudaStreamSynchronize(h->copy[i]);
-    cudaStreamDestroy(h->copy[i]);
-    cudaEventDestroy(h->done[i]);
-  }
-  for (int q = 0; q < STG_MAX_PARTS; ++q) cudaEventDestroy(h->packed[q]);
-  delete h;
-  return STG_OK;
-}
-
-STG_API int stg_exchange_run_f32(void* handle, const float* own, int32_t feat, const int64_t* send_rows,
-                                 const int64_t* send_off, float* send_buf, float* const* peer_dst,
-                                 int32_t* const* peer_flags, const int32_t* seq_values, int32_t value, int32_t num_parts,
-                                 int32_t my_rank, int32_t per_peer_gathers, void* stream) {
-  StgExchange* h = static_cast<StgExchange*>(handle);
-  STG_CHECK_ARG(h != nullptr, "exchange handle is NULL");
-  STG_CHECK_ARG(num_parts >= 1 && num_parts <= STG_MAX_PARTS, "num_parts must be in [1, %d]", STG_MAX_PARTS);
-  STG_CHECK_ARG(my_rank >= 0 && my_rank < num_parts && feat > 0, "bad rank / feat");
-  STG_CHECK_ARG(send_off && peer_dst && peer_flags && seq_values, "NULL argument");
-  STG_CHECK_ARG(value >= 0 && value < 65536, "sequence value must be in [0, 65536)");
-  cudaStream_t s = as_stream(stream);
-  // The peers are served in send order q = rank+1, rank+2, ...; their segments are packed by `groups` gather kernels
-  // (1: one kernel for everything -- the only choice when `stream` runs beside a persistent grid, where a second
-  // launch would starve; P-1: one kernel per peer; in between: the first copies start after 1/groups of the packing).
-  const int peers = num_parts - 1;
-  int groups = per_peer_gathers <= 0 ? 1 : (per_peer_gathers > peers ? peers : per_peer_gathers);
-  if (groups < 1) groups = 1;
-  int done_peers = 0;
-  for (int gi = 0; gi < groups; ++gi) {
-    const int upto = static_cast<int>((static_cast<int64_t>(peers) * (gi + 1)) / groups);
-    // segments of consecutive send-order peers are not contiguous in send_buf (it is ordered by rank): one launch each,
-    // unless the whole buffer is packed at once
-    if (groups == 1) {
-      int rc = stg_rows_gather_f32(own, feat, send_rows, send_off[num_parts], send_buf, 0, s);
-      if (rc != STG_OK) return rc;
-    } else {
-      for (int i = done_peers + 1; i <= upto; ++i) {
-        const int q = (my_rank + i) % num_parts;
-        const int64_t rows = send_off[q + 1] - send_off[q];
-        STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
-        if (rows > 0) {
-          STG_CHECK_ARG(own && send_rows && send_buf, "NULL buffer for a non-empty segment (peer %d)", q);
-          int rc = stg_rows_gather_f32(own, feat, send_rows + send_off[q], rows,
-                                       send_buf + static_cast<size_t>(send_off[q]) * feat, 0, s);
-          if (rc != STG_OK) return rc;
-        }
-      }
-    }
-    STG_CUDA(cudaEventRecord(h->packed[gi], s));
-    for (int i = done_peers + 1; i <= upto; ++i) {
-      const int q = (my_rank + i) % num_parts;
-      const int64_t rows = send_off[q + 1] - send_off[q];
-      STG_CHECK_ARG(rows >= 0, "send_off must be non-decreasing");
-      cudaStream_t cs = h->copy[(i - 1) % h->n_streams];
-      STG_CUDA(cudaStreamWaitEvent(cs, h->packed[gi], 0));
-      if (rows > 0) {
-        STG_CHECK_ARG(send_buf && peer_dst[q], "NULL buffer for a non-empty segment (peer %d)", q);
-        STG_CUDA(cudaMemcpyAsync(peer_dst[q], send_buf + static_cast<size_t>(send_off[q]) * feat,
-                                 static_cast<size_t>(rows) * feat * sizeof(float), cudaMemcpyDeviceToDevice, cs));
-      }
-      if (peer_flags[q] != nullptr)
-        STG_CUDA(cudaMemcpyAsync(peer_flags[q], seq_values + value, sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
-    }
-    done_peers = upto;
-  }
-  return STG_OK;
-}
-
-// Make `stream` wait for every copy enqueued by the last stg_exchange_run_f32 (send_buf may be refilled after it).
-STG_API int stg_exchange_join(void* handle, void* stream) {
-  StgExchange* h = static_cast<StgExchange*>(handle);
-  STG_CHECK_ARG(h != nullptr, "exchange handle is NULL");
-  for (int i = 0; i < h->n_streams; ++i) {
-    STG_CUDA(cudaEventRecord(h->done[i], h->copy[i]));
-    STG_CUDA(cudaStreamWaitEvent(as_stream(stream), h->done[i], 0));
-  }
-  return STG_OK;
-}

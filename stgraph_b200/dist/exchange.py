@@ -3,22 +3,25 @@
 One :class:`HaloExchange` serves one CSR direction of a :class:`~stgraph_b200.dist.partition.PartitionedGraph`
 at one feature width.  Per aggregation (``aggregate``):
 
-    copy streams (owned by the C handle)                  my stream
+    side stream (high priority)                          my stream
     -----------------------------------------------      -------------------------------------------------
-                                                          P-1 gather kernels: the rows peer q needs -> send buffer
-    copy q's segment into q's halo buffer, then a         own-source pass: every local row, edges whose
-      4-byte arrival flag, as soon as it is packed          source row I own (packed {col, scale} metadata,
-      (copy engines; P-1 copies on 3 streams)               global row queue)  ->  out = ...
+    gather the rows my peers need into a send buffer      own-source pass: every local row, edges whose
+    P-1 copy-engine copies into the peers' halo buffers     source row I own (packed {col, scale} metadata,
+    P-1 copy-engine writes of the arrival flags             global row queue)  ->  out = ...
                                                           wait for the P-1 arrival flags (one spinning warp)
                                                           halo-source pass: rows with a remote neighbour,
                                                             out += ... (row-subset form)
 
-No SM copies halo bytes (``stg_halo_send_f32``), so the own-source pass keeps the whole chip; no NCCL and no
-device-wide barrier on the data path: the halo buffers are double-buffered in symmetric memory and the flags
-only grow, which orders "peer q has read buffer k of step t-2" before "I overwrite it at step t" transitively
-(my step t starts after my halo pass t-1, which waited for q's flag t-1, which q posted after its step t-1 sends,
-which q started after its halo pass t-2).  ``mode="sm"`` keeps the round-1 SM push kernel (``stg_halo_push_f32``)
-for A/B runs.  torch is plumbing here: allocation, symmetric-memory rendezvous, streams.
+Only the gather runs on SMs (``stg_halo_exchange_f32``): no SM copies halo bytes over NVLink and nothing on the side
+stream needs an SM slot once the persistent aggregation grid has filled the chip (a one-warp signalling kernel waited
+0.47 ms for one); no NCCL and no device-wide barrier on the data path: the halo buffers are double-buffered in
+symmetric memory and the flags only grow, which orders "peer q has read buffer k of step t-2" before "I overwrite it
+at step t" transitively (my step t starts after my halo pass t-1, which waited for q's flag t-1, which q posted after
+its step t-1 sends, which q started after its halo pass t-2).  Measured alternatives (8 GPUs, config 5): the round-1 SM
+push kernel (``mode="sm"``, kept for A/B runs) 0.5-0.78 ms per exchange and the own-source pass slowed from 0.32 to
+0.6 ms; per-peer gather kernels feeding copies on three private streams, gathers ahead of the aggregation pass: no
+faster at 8 ranks (1.33-1.35 vs 1.31 ms/step), slower at 4 (2.02 vs 1.74 ms/step) -- removed.  torch is plumbing here:
+allocation, symmetric-memory rendezvous, streams.
 """
 from __future__ import annotations
 
@@ -90,11 +93,9 @@ class HaloExchange:
             within = torch.arange(n_send, device=dev, dtype=torch.int64) - seg[peer]
             self._send_peer = peer.to(torch.int32).contiguous()
             self._send_slot = (torch.as_tensor(dst_off, dtype=torch.int64, device=dev)[peer] + within).contiguous()
-        self._handle = ctypes.c_void_p()
-        _lib.call("stg_exchange_create", int(os.environ.get("STG_COPY_STREAMS", "3")), ctypes.byref(self._handle))
         self.side = torch.cuda.Stream(device=dev, priority=-1)
         self._ev_in = torch.cuda.Event()
-        self._ev_gathered = torch.cuda.Event()
+        self._ev_sent = torch.cuda.Event()
         self._iter = 0
         # the two sub-CSRs of my rows with their packed {col, scale} metadata (scales are fixed per graph: norm)
         self.v_own, _ = plan.split_views()
@@ -103,14 +104,6 @@ class HaloExchange:
         self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, None, device=dev)
                           if plan.halo_cols.numel() else None)
         self.ns_own, self.ns_halo = ns_own, ns_halo
-        # which leg is longer?  exchange: halo bytes in at ~600 GB/s; own-source pass: ~25 edges/ns (measured, F=100)
-        t_x = max(plan.n_halo, n_send) * self.feat * 4 / 600e9
-        t_own = int(plan.own_cols.numel()) * (self.feat / 100.0) / 25e9
-        gf = os.environ.get("STG_GATHER_FIRST")
-        self.gather_first = (t_x > 0.8 * t_own) if gf is None else gf == "1"
-        # number of gather launches (measured at 8 GPUs: seven per-peer kernels take 0.13 ms, twice one kernel's time,
-        # and buy nothing; two groups let the first copies start after half of the packing)
-        self.per_peer_gathers = int(os.environ.get("STG_GATHER_GROUPS", "2")) if self.gather_first else 1
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:
@@ -130,37 +123,39 @@ class HaloExchange:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)] if self.profile is not None else None
         if ev:
             ev[0].record(cur)
-            ev[4].record(cur)
+        self._ev_in.record(cur)
+        side.wait_event(self._ev_in)
         n_send = int(plan.send_index.numel())
-        if self.mode == "sm":
-            self._ev_in.record(cur)
-            side.wait_event(self._ev_in)
-            with torch.cuda.stream(side):
+        with torch.cuda.stream(side):
+            if ev:
+                ev[4].record(side)
+            if self.mode == "sm":
                 if n_send:
                     _lib.call("stg_halo_push_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(),
                               self._send_peer.data_ptr(), self._send_slot.data_ptr(), n_send, self._peer_halo[k], world,
                               self.push_blocks, side.cuda_stream)
-                _lib.call("stg_peer_signal", self._peer_flag[k], world, rank, it & 0xFFFF, side.cuda_stream)
-                self._ev_gathered.record(side)
                 if ev:
                     ev[5].record(side)
                     ev[6].record(side)
-        else:
-            # per-peer gathers, copies + flags on the handle's copy streams.  When the exchange is the longer leg (8
-            # ranks) the gathers run on MY stream and finish before the aggregation pass starts (0.06 ms with the
-            # whole chip); when the own-source pass is the longer leg (2-4 ranks) they run beside it on a side stream.
-            gs = cur if self.gather_first else side
-            if not self.gather_first:
-                self._ev_in.record(cur)
-                side.wait_event(self._ev_in)
-            _lib.call("stg_exchange_run_f32", self._handle, x_own.data_ptr(), self.feat, plan.send_index.data_ptr(),
-                      self._send_off, self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(),
-                      it & 0xFFFF, world, rank, self.per_peer_gathers, gs.cuda_stream)
-            if ev:
-                ev[5].record(gs)
-                _lib.call("stg_exchange_join", self._handle, side.cuda_stream)
+                _lib.call("stg_peer_signal", self._peer_flag[k], world, rank, it & 0xFFFF, side.cuda_stream)
+            elif ev:          # profiling: the three steps one by one, with an event between them
+                _lib.call("stg_rows_gather_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), n_send,
+                          self.send_buf.data_ptr(), self.gather_blocks, side.cuda_stream)
+                ev[5].record(side)
+                _lib.call("stg_halo_send_f32", self.send_buf.data_ptr(), self.feat, world, rank, self._send_off,
+                          self._peer_dst[k], side.cuda_stream)
                 ev[6].record(side)
-        # the edges whose source I own
+                _lib.call("stg_halo_exchange_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), self._zero_off,
+                          self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(), it & 0xFFFF,
+                          world, rank, self.gather_blocks, side.cuda_stream)        # no rows: the flag copies only
+            else:
+                _lib.call("stg_halo_exchange_f32", x_own.data_ptr(), self.feat, plan.send_index.data_ptr(), self._send_off,
+                          self.send_buf.data_ptr(), self._peer_dst[k], self._peer_flag[k], self._seq.data_ptr(), it & 0xFFFF,
+                          world, rank, self.gather_blocks, side.cuda_stream)
+            self._ev_sent.record(side)
+            if ev:
+                ev[7].record(side)
+        # my stream: the edges whose source I own (launched right behind the gather: the two run side by side)
         if self.meta_own is not None:
             kernels.agg_packed_sum_rows(self.v_own, self.meta_own, None, x_own, rs, out, accumulate=False)
         else:
@@ -174,11 +169,8 @@ class HaloExchange:
         if self.meta_halo is not None:
             kernels.agg_packed_sum_rows(self.v_halo, self.meta_halo, plan.halo_out_rows, self.halo_rows(k), rs, out,
                                         accumulate=True)
-        if self.mode == "sm":
-            cur.wait_event(self._ev_gathered)      # x_own may be reused by the caller from here on
-        else:
-            _lib.call("stg_exchange_join", self._handle, cur.cuda_stream)     # my copies have drained: send_buf is free
-        kernels.launch_count += 2 + (world - 1 if self.mode != "sm" else 1)   # gathers (or push + signal) + wait kernel
+        cur.wait_event(self._ev_sent)       # my sends have drained: x_own and the send buffer may be reused from here on
+        kernels.launch_count += 3 if self.mode == "sm" else 2       # gather (or push + signal) + wait kernel of this call
         if ev:
             ev[3].record(cur)
             self.profile.append(ev)
@@ -193,17 +185,7 @@ class HaloExchange:
     def profile_summary(self):
         """Mean device time (ms) of the segments of ``aggregate`` (set ``self.profile = []`` to collect)."""
         torch.cuda.synchronize()
-        seg = {"gather_or_push": (4, 5), "own_pass": (5, 1), "wait_flags": (1, 2), "halo_pass": (2, 3), "total": (0, 3),
-               "sends_done_after_start": (4, 6)}
-        if self.mode == "sm" or not self.gather_first:
-            seg["own_pass"] = (0, 1)
+        seg = {"own_pass": (0, 1), "wait_flags": (1, 2), "halo_pass": (2, 3), "total": (0, 3), "gather_or_push": (4, 5),
+               "send": (5, 6), "flags": (6, 7), "exchange_total": (4, 7)}
         n = max(len(self.profile), 1)
         return {name: sum(e[a].elapsed_time(e[b]) for e in self.profile) / n for name, (a, b) in seg.items()}
-
-    def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None and self._handle.value:
-                _lib.call("stg_exchange_destroy", self._handle)
-                self._handle = None
-        except Exception:
-            pass
