@@ -173,8 +173,7 @@ int stg_halo_push_f32(const float* own, int32_t feat, const int64_t* send_rows, 
  *   stg_peer_signal     : after everything enqueued so far on `stream`, write `value` to *peer_flags[q] for every
  *                         q != my_rank (release, system scope);
  *   stg_peer_wait       : block `stream` (a one-warp spinning kernel) until flags[q] has reached value (compared
- *                         modulo 2^16: ((flags[q] - value) & 0xFFFF) < 0x8000) for every q != my_rank whose bit is set in
- *                         peer_mask (0 = every peer)
+ *                         modulo 2^16: ((flags[q] - value) & 0xFFFF) < 0x8000) for every q != my_rank
  *                         (acquire, system scope); gives up after timeout_cycles SM clocks
  *                         (<= 0: 2^32) and then sets *status = 1 + q (status may be NULL).
  * No SM takes part in the transfer itself, so it overlaps the own-source aggregation pass for free. */
@@ -190,8 +189,8 @@ int stg_halo_exchange_f32(const float* own, int32_t feat, const int64_t* send_ro
                           float* send_buf, float* const* peer_dst, int32_t* const* peer_flags, const int32_t* seq_values,
                           int32_t value, int32_t num_parts, int32_t my_rank, int32_t gather_blocks, void* stream);
 int stg_peer_signal(int32_t* const* peer_flags, int32_t num_parts, int32_t my_rank, int32_t value, void* stream);
-int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, uint32_t peer_mask,
-                  int64_t timeout_cycles, int32_t* status, void* stream);
+int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, int64_t timeout_cycles,
+                  int32_t* status, void* stream);
 
 /* Same operation with HOST buffers: copies x (and the scale vectors) to the
  * device scratch the caller provides, runs the kernel, copies out back.

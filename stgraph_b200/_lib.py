@@ -104,7 +104,7 @@ _SIGNATURES = {
     "stg_halo_exchange_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, _P(c_int64), c_void_p, _P(c_void_p), _P(c_void_p),
                                               c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p], True),
     "stg_peer_signal": (ctypes.c_int, [_P(c_void_p), c_int32, c_int32, c_int32, c_void_p], True),
-    "stg_peer_wait": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, ctypes.c_uint32, c_int64, c_void_p, c_void_p], True),
+    "stg_peer_wait": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p], True),
     "stg_agg_scaled_sum_parts_f32": (ctypes.c_int, [_P(StgCsrView), _P(c_void_p), _P(c_int32), c_int32, c_int32, c_void_p,
                                                     c_void_p, c_void_p, c_void_p, c_void_p], True),
     "stg_halo_pull_f32": (ctypes.c_int, [_P(c_void_p), _P(c_int32), c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32,

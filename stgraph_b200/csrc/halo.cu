@@ -165,10 +165,10 @@ __global__ void peer_signal_kernel(const SignalParams p) {
 
 // Spin until every peer's flag has reached `value` (flags only grow).  Gives up after `timeout_cycles` SM
 // clocks and raises *status so that a lost peer cannot hang the device (the host checks status later).
-__global__ void peer_wait_kernel(const int32_t* flags, int nparts, int rank, int value, unsigned peer_mask,
-                                 long long timeout_cycles, int32_t* status) {
+__global__ void peer_wait_kernel(const int32_t* flags, int nparts, int rank, int value, long long timeout_cycles,
+                                 int32_t* status) {
   const int q = threadIdx.x;
-  if (q < nparts && q != rank && ((peer_mask >> q) & 1u)) {
+  if (q < nparts && q != rank) {
     const long long t0 = clock64();
     int v;
     for (;;) {
@@ -232,11 +232,11 @@ STG_API int stg_peer_signal(int32_t* const* peer_flags, int32_t num_parts, int32
   return STG_OK;
 }
 
-STG_API int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, uint32_t peer_mask,
-                          int64_t timeout_cycles, int32_t* status, void* stream) {
+STG_API int stg_peer_wait(const int32_t* flags, int32_t num_parts, int32_t my_rank, int32_t value, int64_t timeout_cycles,
+                          int32_t* status, void* stream) {
   STG_CHECK_ARG(num_parts >= 1 && num_parts <= STG_MAX_PARTS, "num_parts must be in [1, %d]", STG_MAX_PARTS);
   STG_CHECK_ARG(flags && my_rank >= 0 && my_rank < num_parts, "bad arguments");
-  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(flags, num_parts, my_rank, value, peer_mask ? peer_mask : 0xFFFFFFFFu,
+  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(flags, num_parts, my_rank, value,
                                                      timeout_cycles > 0 ? timeout_cycles : (4LL << 30), status);
   STG_LAUNCH_CHECK("peer_wait_kernel");
   return STG_OK;

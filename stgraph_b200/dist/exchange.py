@@ -20,7 +20,9 @@ at step t" transitively (my step t starts after my halo pass t-1, which waited f
 its step t-1 sends, which q started after its halo pass t-2).  Measured alternatives (8 GPUs, config 5): the round-1 SM
 push kernel (``mode="sm"``, kept for A/B runs) 0.5-0.78 ms per exchange and the own-source pass slowed from 0.32 to
 0.6 ms; per-peer gather kernels feeding copies on three private streams, gathers ahead of the aggregation pass: no
-faster at 8 ranks (1.33-1.35 vs 1.31 ms/step), slower at 4 (2.02 vs 1.74 ms/step) -- removed.  torch is plumbing here:
+faster at 8 ranks (1.33-1.35 vs 1.31 ms/step), slower at 4 (2.02 vs 1.74 ms/step) -- removed; the halo-source pass
+split by arrival order of the owners (first half of the peers while the second half is still on the wire): 1.41 ms/step
+with two groups, 1.63 with three, against 1.26 with one pass -- every extra pass revisits the rows -- removed.  torch is plumbing here:
 allocation, symmetric-memory rendezvous, streams.
 """
 from __future__ import annotations
@@ -104,17 +106,6 @@ class HaloExchange:
         self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, None, device=dev)
                           if plan.halo_cols.numel() else None)
         self.ns_own, self.ns_halo = ns_own, ns_halo
-        # When the exchange outlasts the own-source pass (8 ranks: 186 MB in at ~550 GB/s against 0.3 ms of work) the
-        # halo-source pass is split by arrival order of the owners: the first half runs while the second half is
-        # still on the wire.  Halo bytes in at ~550 GB/s vs own-source edges at ~25 per ns (measured, F=100).
-        t_x = max(plan.n_halo, n_send) * self.feat * 4 / 550e9
-        t_own = int(plan.own_cols.numel()) * (self.feat / 100.0) / 25e9
-        env = os.environ.get("STG_HALO_GROUPS")
-        n_groups = int(env) if env else (2 if (t_x > 1.1 * t_own and world >= 4) else 1)
-        self.groups = None
-        if n_groups > 1 and plan.halo_cols.numel():
-            self.groups = [(v, rows, mask, kernels.pack_edge_meta(v, ns_halo, None, device=dev))
-                           for v, rows, mask, n_e in plan.halo_group_views(n_groups) if n_e > 0]
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:
@@ -173,22 +164,13 @@ class HaloExchange:
             out.zero_()
         if ev:
             ev[1].record(cur)
-        if self.groups is None:
-            _lib.call("stg_peer_wait", self._flags.data_ptr() + k * 16 * 4, world, rank, it & 0xFFFF, 0, WAIT_TIMEOUT_CYCLES,
-                      self.status.data_ptr(), cur.cuda_stream)
-            if ev:
-                ev[2].record(cur)
-            if self.meta_halo is not None:
-                kernels.agg_packed_sum_rows(self.v_halo, self.meta_halo, plan.halo_out_rows, self.halo_rows(k), rs, out,
-                                            accumulate=True)
-        else:
-            for gi, (view, out_rows, mask, meta) in enumerate(self.groups):
-                _lib.call("stg_peer_wait", self._flags.data_ptr() + k * 16 * 4, world, rank, it & 0xFFFF, mask,
-                          WAIT_TIMEOUT_CYCLES, self.status.data_ptr(), cur.cuda_stream)
-                if ev and gi == 0:
-                    ev[2].record(cur)
-                kernels.agg_packed_sum_rows(view, meta, out_rows, self.halo_rows(k), rs, out, accumulate=True)
-                kernels.launch_count += 1 if gi else 0
+        _lib.call("stg_peer_wait", self._flags.data_ptr() + k * 16 * 4, world, rank, it & 0xFFFF, WAIT_TIMEOUT_CYCLES,
+                  self.status.data_ptr(), cur.cuda_stream)
+        if ev:
+            ev[2].record(cur)
+        if self.meta_halo is not None:
+            kernels.agg_packed_sum_rows(self.v_halo, self.meta_halo, plan.halo_out_rows, self.halo_rows(k), rs, out,
+                                        accumulate=True)
         cur.wait_event(self._ev_sent)       # my sends have drained: x_own and the send buffer may be reused from here on
         kernels.launch_count += 3 if self.mode == "sm" else 2       # gather (or push + signal) + wait kernel of this call
         if ev:

@@ -76,7 +76,6 @@ class HaloPlan:
         recv_counts = (split[1:] - split[:-1]).to(torch.int64)
         send_counts = torch.empty_like(recv_counts)
         dist.all_to_all_single(send_counts, recv_counts, group=group)
-        self._halo_split = split                                          # halo_ids[split[q]:split[q+1]] are owned by rank q
         self.out_splits = [int(v) for v in recv_counts.cpu()]            # rows I receive from each owner
         self.in_splits = [int(v) for v in send_counts.cpu()]             # rows I send to each requester
         send_ids = torch.empty(sum(self.in_splits), dtype=torch.int64, device=dev)
@@ -148,40 +147,6 @@ class HaloPlan:
             self._compact_view = self._make_view(self.halo_compact_ro, self.halo_cols, self.halo_eids,
                                                  n_rows=int(self.halo_out_rows.numel()))
         return self._compact_view
-
-    def halo_group_views(self, n_groups: int):
-        """The halo-source edges split by ARRIVAL ORDER of their owner: ``[(view, out_rows, peer_mask)]``.
-
-        Every rank sends to ``rank+1, rank+2, ...`` in that order, so the rows of ``rank-1`` land first and those of
-        ``rank+1`` last.  With the peers cut into ``n_groups`` arrival groups, the halo-source pass over group 0 can run
-        while the later groups are still on the wire (only worth it when the exchange outlasts the own-source pass:
-        8 ranks).  View row ``i`` of group g is local row ``out_rows[i]``; within a row the edges keep their order,
-        and the groups are added in a fixed order, so the result stays deterministic."""
-        key = int(n_groups)
-        cache = self.__dict__.setdefault("_group_views", {})
-        if key in cache:
-            return cache[key]
-        dev = self.halo_cols.device
-        order = [(self.rank - i) % self.world for i in range(1, self.world)]
-        per = -(-len(order) // max(key, 1))
-        groups = [order[k * per:(k + 1) * per] for k in range(key) if order[k * per:(k + 1) * per]]
-        owner = torch.bucketize(self.halo_cols.to(torch.int64), self._halo_split[1:-1].to(torch.int64), right=True)
-        hdeg = (self.halo_ro[1:] - self.halo_ro[:-1]).to(torch.int64)
-        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=dev, dtype=torch.int64), hdeg)
-        out = []
-        for g in groups:
-            mask = torch.isin(owner, torch.as_tensor(g, dtype=torch.int64, device=dev))
-            cnt = torch.bincount(rows[mask], minlength=self.n_rows)
-            sel = torch.nonzero(cnt > 0).reshape(-1)
-            cro = torch.zeros(sel.numel() + 1, dtype=torch.int32, device=dev)
-            cro[1:] = torch.cumsum(cnt[sel], 0).to(torch.int32)
-            cols, eids = self.halo_cols[mask].contiguous(), self.halo_eids[mask].contiguous()
-            out_rows = sel.to(torch.int32).contiguous()
-            self._keep.append((cro, cols, eids, out_rows))
-            view = self._make_view(cro, cols, eids, n_rows=int(sel.numel()))
-            out.append((view, out_rows, sum(1 << q for q in g), int(cols.numel())))
-        cache[key] = out
-        return out
 
     def new_halo_buffer(self, feat: int, like: torch.Tensor) -> torch.Tensor:
         return torch.empty(max(self.n_halo, 1), feat, dtype=like.dtype, device=like.device)[:self.n_halo]
