@@ -315,8 +315,7 @@ def main():
                                     "arrival flags, then the halo-source pass; no NCCL on the data path"}[ex_f.mode],
                      "halo_rows_fwd": hf.n_halo, "halo_rows_bwd": ex_b.plan.n_halo, "own_rows": pg.n_own,
                      "full_allgather_rows": n - pg.n_own, "halo_edges_fwd": int(hf.halo_cols.shape[0]),
-                     "own_edges_fwd": int(hf.own_cols.shape[0]), "bounds": pg.bounds,
-                     "visit_schedule_fwd": ex_f.schedule_stats}
+                     "own_edges_fwd": int(hf.own_cols.shape[0]), "bounds": pg.bounds}
         del x, gout
 
         def step(ev=None):

@@ -141,14 +141,6 @@ int stg_agg_scaled_sum_rows_f32(const StgCsrView* g, const int32_t* out_rows, co
 int stg_agg_packed_sum_rows_f32(const StgCsrView* g, const StgEdgeMeta* meta, const int32_t* out_rows, const float* x,
                                 int32_t feat, const float* row_scale, float* out, int32_t accumulate, void* stream);
 
-/* The same with TWO source matrices: a packed column c < split_col reads x[c,:], a column c >= split_col reads
- * x2[c - split_col,:].  A rank of the row-partitioned graph uses it to sum the own-source AND the halo-source edges
- * of a row in one visit (x = the rows it owns, x2 = the halo rows its peers sent), for the rows it walks after the
- * halo has landed. */
-int stg_agg_packed_sum_rows2_f32(const StgCsrView* g, const StgEdgeMeta* meta, const int32_t* out_rows, const float* x,
-                                 const float* x2, int32_t split_col, int32_t feat, const float* row_scale, float* out,
-                                 int32_t accumulate, void* stream);
-
 /* Same operation with the source matrix ROW-PARTITIONED into num_parts blocks (multi-GPU): block q holds
  * rows [part_bounds[q], part_bounds[q+1]) of x and may live in a peer GPU's memory mapped into this
  * process (CUDA IPC / symmetric memory): the kernel then fetches remote neighbour rows with NVLink

@@ -99,8 +99,6 @@ _SIGNATURES = {
                                          c_int32, c_void_p], True),
     "stg_agg_packed_sum_rows_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                                    c_void_p, c_int32, c_void_p], True),
-    "stg_agg_packed_sum_rows2_f32": (ctypes.c_int, [_P(StgCsrView), c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                                    c_void_p, c_void_p, c_int32, c_void_p], True),
     "stg_rows_gather_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p], True),
     "stg_halo_send_f32": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, _P(c_int64), _P(c_void_p), c_void_p], True),
     "stg_halo_exchange_f32": (ctypes.c_int, [c_void_p, c_int32, c_void_p, _P(c_int64), c_void_p, _P(c_void_p), _P(c_void_p),

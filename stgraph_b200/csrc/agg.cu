@@ -53,8 +53,6 @@ struct AggParams {
   const int32_t* __restrict__ hub_count;
   const int32_t* __restrict__ out_rows;   // view row -> output row (NULL: identity)
   const int2* __restrict__ meta;          // PACKED mode: {column, scale bits} of every CSR slot (stg_csr_pack_edge_meta_f32)
-  const float* __restrict__ x2;           // kPacked2: second source matrix (already offset to the chunk's first column)
-  int split_col;                          // kPacked2: columns >= split_col live in x2, at row (column - split_col)
   int* queue;                             // global row queue {next chunk, finished blocks} (StgCsrView::work_queue) or NULL
   int num_rows;
   int num_edges;
@@ -98,11 +96,7 @@ __device__ __forceinline__ const float* src_row(const AggParams& p, int c) {
 //            (stg_csr_pack_edge_meta_f32).  The scattered 4-byte nbr_scale gather costs one 32-byte L2 sector
 //            request per edge -- as many requests as a quarter of the 400..512-byte neighbour row itself -- and
 //            one level of the dependent load chain; a static graph with a fixed norm pays for the packing once.
-//   kPacked2 kPacked with TWO source matrices: columns below `split_col` index x, the others x2 (shifted by split_col) --
-//            a rank of the row-partitioned graph sums a row's own-source and halo-source edges in ONE visit
-//            (rows it owns | halo rows received from the peers), stg_agg_packed_sum_rows2_f32.
-enum AggMode { kPlain = 0, kParts = 1, kPacked = 2, kPacked2 = 3 };
-__host__ __device__ constexpr bool is_packed(int mode) { return mode == kPacked || mode == kPacked2; }
+enum AggMode { kPlain = 0, kParts = 1, kPacked = 2 };
 
 // Column index (and, kPacked, the scale `ms`) of edge `base + gl` (0 / 0.f past the end of the row).
 template <int MODE>
@@ -111,7 +105,7 @@ __device__ __forceinline__ void load_col(const AggParams& p, int base, int end, 
   ms = 0.f;
   const int e = base + gl;
   if (e < end) {
-    if constexpr (is_packed(MODE)) {
+    if constexpr (MODE == kPacked) {
       const int2 m = __ldcs(p.meta + e);
       c = m.x;
       ms = __int_as_float(m.y);
@@ -123,7 +117,7 @@ __device__ __forceinline__ void load_col(const AggParams& p, int base, int end, 
 // Combined scale of edge `base + gl` whose column `c` has arrived (0.f past the end of the row).
 template <int MODE>
 __device__ __forceinline__ void load_scale(const AggParams& p, int base, int end, int gl, int c, float ms, float& s) {
-  if constexpr (is_packed(MODE)) {
+  if constexpr (MODE == kPacked) {
     s = ms;
     return;
   }
@@ -150,7 +144,6 @@ template <int VEC, int GROUP, int NACC, int MODE>
 struct RowLoader {
   using T = typename VecT<VEC>::type;
   const char* base[NACC];
-  long long delta2;        // kPacked2: byte distance from a chunk of x's row c to the same chunk of x2's row (c - split_col)
   int off[NACC];
   bool live[NACC];        // lane-constant: this lane's chunk k lies inside the row
   unsigned ld_bytes;
@@ -164,9 +157,6 @@ struct RowLoader {
       off[k] = o;
       base[k] = reinterpret_cast<const char*>(p.x + o);
     }
-    delta2 = 0;
-    if constexpr (MODE == kPacked2)
-      delta2 = (reinterpret_cast<const char*>(p.x2) - reinterpret_cast<const char*>(p.x)) - static_cast<long long>(p.split_col) * ld_bytes;
   }
   // Idle lanes (F=100: lanes 25..31) are predicated off with a loop-invariant predicate: a lane that does not
   // load costs no LSU write-back slot, and the write-back of 32 x 16 bytes per row is what bounds F = 68..124.
@@ -176,11 +166,7 @@ struct RowLoader {
     if constexpr (MODE == kParts) {
       v = ld_row<VEC>(src_row(p, c) + off[k]);
     } else {
-      if (live[k]) {
-        const char* a = base[k] + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes;
-        if constexpr (MODE == kPacked2) a += (c >= p.split_col) ? delta2 : 0ll;
-        v = __ldg(reinterpret_cast<const T*>(a));
-      }
+      if (live[k]) v = __ldg(reinterpret_cast<const T*>(base[k] + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
     }
     return v;
   }
@@ -338,20 +324,10 @@ __device__ __forceinline__ void accumulate_edges_pair(const AggParams& p, int be
     base1 = reinterpret_cast<const char*>(p.x + o1);
   }
   const bool live1 = (hl + 16) * 4 < p.width;   // chunk 0 is always inside the row (width > 64); F=100: 9 of 16 lanes
-  // kPacked2: byte distance from a chunk of x's row c to the same chunk of x2's row (c - split_col): lane-independent
-  long long d2 = 0;
-  if constexpr (MODE == kPacked2)
-    d2 = (reinterpret_cast<const char*>(p.x2) - reinterpret_cast<const char*>(p.x)) - static_cast<long long>(p.split_col) * ld_bytes;
-  auto row0 = [&](int c) {
-    const char* a = base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes;
-    if constexpr (MODE == kPacked2) a += (c >= p.split_col) ? d2 : 0ll;
-    return ldg_row(reinterpret_cast<const float4*>(a));
-  };
+  auto row0 = [&](int c) { return ldg_row(reinterpret_cast<const float4*>(base0 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes)); };
   auto row1 = [&](int c) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const char* a = base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes;
-    if constexpr (MODE == kPacked2) a += (c >= p.split_col) ? d2 : 0ll;
-    if (live1) v = ldg_row(reinterpret_cast<const float4*>(a));
+    if (live1) v = ldg_row(reinterpret_cast<const float4*>(base1 + static_cast<unsigned long long>(static_cast<unsigned>(c)) * ld_bytes));
     return v;
   };
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
@@ -871,10 +847,8 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
                           const float* es, const float* rs, float* out, cudaStream_t stream,
                           int nparts = 0, const float* const* parts = nullptr, const int32_t* bounds = nullptr,
                           int accumulate = 0, const int32_t* out_rows = nullptr, const StgEdgeMeta* meta = nullptr,
-                          int x_ld = 0, int out_ld = 0, const float* x2 = nullptr, int split_col = 0) {
+                          int x_ld = 0, int out_ld = 0) {
   AggParams p;
-  p.x2 = nullptr;
-  p.split_col = split_col;
   p.out_rows = out_rows;
   p.meta = reinterpret_cast<const int2*>(meta);
   p.queue = g->work_queue;
@@ -900,8 +874,8 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   p.rs = rs;
   bool al16 = aligned16(out), al8 = aligned8(out);
   if (nparts == 0) {
-    al16 = al16 && aligned16(x) && (x2 == nullptr || aligned16(x2));
-    al8 = al8 && aligned8(x) && (x2 == nullptr || aligned8(x2));
+    al16 = al16 && aligned16(x);
+    al8 = al8 && aligned8(x);
   }
   for (int q = 0; q < nparts; ++q) {
     al16 = al16 && aligned16(parts[q]);
@@ -913,7 +887,6 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   const int chunk = 32 * 4 * vec;  // widest tile one launch covers
   for (int f0 = 0; f0 < feat; f0 += chunk) {
     p.x = x ? x + f0 : nullptr;
-    p.x2 = x2 ? x2 + f0 : nullptr;
     for (int q = 0; q < nparts; ++q) p.xs[q] = parts[q] + f0;
     p.out = out + f0;
     p.width = min(chunk, feat - f0);
@@ -923,10 +896,6 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
       if (vec == 4) rc = dispatch_group<4, kParts>(p, stream, avg_degree);
       else if (vec == 2) rc = dispatch_group<2, kParts>(p, stream, avg_degree);
       else rc = dispatch_group<1, kParts>(p, stream, avg_degree);
-    } else if (meta != nullptr && x2 != nullptr) {
-      if (vec == 4) rc = dispatch_group<4, kPacked2>(p, stream, avg_degree);
-      else if (vec == 2) rc = dispatch_group<2, kPacked2>(p, stream, avg_degree);
-      else rc = dispatch_group<1, kPacked2>(p, stream, avg_degree);
     } else if (meta != nullptr) {
       if (vec == 4) rc = dispatch_group<4, kPacked>(p, stream, avg_degree);
       else if (vec == 2) rc = dispatch_group<2, kPacked>(p, stream, avg_degree);
@@ -1130,22 +1099,4 @@ STG_API int stg_agg_packed_sum_rows_f32(const StgCsrView* g, const StgEdgeMeta* 
   STG_CHECK_ARG(x != out, "x and out must not alias");
   return agg_scaled_sum_device(g, x, feat, nullptr, nullptr, row_scale, out, as_stream(stream), 0, nullptr, nullptr,
                                accumulate, out_rows, g->num_edges == 0 ? nullptr : meta);
-}
-
-STG_API int stg_agg_packed_sum_rows2_f32(const StgCsrView* g, const StgEdgeMeta* meta, const int32_t* out_rows,
-                                         const float* x, const float* x2, int32_t split_col, int32_t feat,
-                                         const float* row_scale, float* out, int32_t accumulate, void* stream) {
-  int rc = validate_view(g, false);
-  if (rc != STG_OK) return rc;
-  STG_CHECK_ARG(feat > 0, "feat must be positive (got %d)", feat);
-  STG_CHECK_ARG(accumulate >= 0 && accumulate <= 2, "accumulate must be 0, 1 or 2 (got %d)", accumulate);
-  STG_CHECK_ARG(split_col >= 0, "split_col must be non-negative (got %d)", split_col);
-  if (g->num_nodes == 0) return STG_OK;
-  STG_CHECK_ARG(g->num_edges == 0 || (meta != nullptr && aligned8(meta)),
-                "meta must be a non-NULL, 8-byte aligned device pointer");
-  STG_CHECK_ARG(x != nullptr && x2 != nullptr && out != nullptr, "x / x2 / out is NULL");
-  STG_CHECK_ARG(x != out && x2 != out, "x / x2 and out must not alias");
-  return agg_scaled_sum_device(g, x, feat, nullptr, nullptr, row_scale, out, as_stream(stream), 0, nullptr, nullptr,
-                               accumulate, out_rows, g->num_edges == 0 ? nullptr : meta, 0, 0,
-                               g->num_edges == 0 ? nullptr : x2, split_col);
 }

@@ -99,28 +99,13 @@ class HaloExchange:
         self._ev_in = torch.cuda.Event()
         self._ev_sent = torch.cuda.Event()
         self._iter = 0
+        # the two sub-CSRs of my rows with their packed {col, scale} metadata (scales are fixed per graph: norm)
+        self.v_own, _ = plan.split_views()
+        self.v_halo = plan.halo_compact_view()
+        self.meta_own = kernels.pack_edge_meta(self.v_own, ns_own, None, device=dev) if plan.own_cols.numel() else None
+        self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, None, device=dev)
+                          if plan.halo_cols.numel() else None)
         self.ns_own, self.ns_halo = ns_own, ns_halo
-        # Visit schedule (HaloPlan.visit_schedule): phase 1 runs beside the exchange -- rows without a remote neighbour in
-        # full, plus the own-source edges of as many other rows as it takes to fill the exchange time; phase 2, after the
-        # flags: the remaining rows in ONE visit over [own | halo] columns, and the halo-source edges of the rows phase 1
-        # started.  Exchange time: packing at ~2.4 TB/s (read + write) + halo bytes in at 780 - 33 (P - 1) GB/s (measured:
-        # 744 / 665 / 550 GB/s at 2 / 4 / 8 ranks); own-source pass: ~30 work units (edges + 4 rows) per ns at F = 100.
-        bw = max(780e9 - 33e9 * (world - 1), 300e9)
-        t_x = 2 * n_send * self.feat * 4 / 2.4e12 + plan.n_halo * self.feat * 4 / bw
-        units = 30e9 * (100.0 / max(self.feat, 25)) * t_x
-        env = os.environ.get("STG_FIRST_PHASE_UNITS")
-        sched = plan.visit_schedule(float(env) if env else units)
-        self.schedule_stats = dict(plan.schedule_stats, exchange_ms_estimate=t_x * 1e3)
-        ns_all = None if ns_own is None else torch.cat([ns_own, ns_halo if ns_halo is not None else ns_own[:0]])
-        pack = lambda v, ns: kernels.pack_edge_meta(v, ns, None, device=dev)
-        self.first = sched["first"][:2] + (pack(sched["first"][0], ns_own),) if sched["first"][2] else None
-        self.second_all = (sched["second_all"][:2] + (pack(sched["second_all"][0], ns_all),)
-                           if sched["second_all"] and sched["second_all"][2] else None)
-        self.second_all_rows = sched["second_all"][1] if sched["second_all"] else None
-        self.second_halo = (sched["second_halo"][:2] + (pack(sched["second_halo"][0], ns_halo),)
-                            if sched["second_halo"] and sched["second_halo"][2] else None)
-        self.first_rows = sched["first"][1]
-        self._n_first_rows = int(self.first_rows.numel())
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)
 
     def halo_rows(self, k: int) -> torch.Tensor:
@@ -172,27 +157,20 @@ class HaloExchange:
             self._ev_sent.record(side)
             if ev:
                 ev[7].record(side)
-        # my stream, phase 1 (launched right behind the gather: the two run side by side): rows that do not wait
-        if self.first is not None:
-            view, rows, meta = self.first
-            kernels.agg_packed_sum_rows(view, meta, rows, x_own, rs, out, accumulate=False)
-        if self._n_first_rows and self.first is None:
-            out.index_fill_(0, self.first_rows.long(), 0.0)      # phase-1 rows without a single edge
+        # my stream: the edges whose source I own (launched right behind the gather: the two run side by side)
+        if self.meta_own is not None:
+            kernels.agg_packed_sum_rows(self.v_own, self.meta_own, None, x_own, rs, out, accumulate=False)
+        else:
+            out.zero_()
         if ev:
             ev[1].record(cur)
         _lib.call("stg_peer_wait", self._flags.data_ptr() + k * 16 * 4, world, rank, it & 0xFFFF, WAIT_TIMEOUT_CYCLES,
                   self.status.data_ptr(), cur.cuda_stream)
         if ev:
             ev[2].record(cur)
-        halo = self.halo_rows(k)
-        if self.second_halo is not None:          # second visit of the rows phase 1 started: out += halo-source edges
-            view, rows, meta = self.second_halo
-            kernels.agg_packed_sum_rows(view, meta, rows, halo, rs, out, accumulate=True)
-        if self.second_all is not None:           # the other rows, once, over all their edges
-            view, rows, meta = self.second_all
-            kernels.agg_packed_sum_rows2(view, meta, rows, x_own, halo, plan.n_own, rs, out, accumulate=False)
-        elif self.second_all_rows is not None and self.second_all_rows.numel():
-            out.index_fill_(0, self.second_all_rows.long(), 0.0)
+        if self.meta_halo is not None:
+            kernels.agg_packed_sum_rows(self.v_halo, self.meta_halo, plan.halo_out_rows, self.halo_rows(k), rs, out,
+                                        accumulate=True)
         cur.wait_event(self._ev_sent)       # my sends have drained: x_own and the send buffer may be reused from here on
         kernels.launch_count += 3 if self.mode == "sm" else 2       # gather (or push + signal) + wait kernel of this call
         if ev:

@@ -148,73 +148,6 @@ class HaloPlan:
                                                  n_rows=int(self.halo_out_rows.numel()))
         return self._compact_view
 
-    # ------------------------------------------------------- visit schedule: who waits for the halo, who does not
-    def visit_schedule(self, first_phase_work: float):
-        """:meth:`visit_schedule_arrays` as C-ABI views: ``{name: (view, out_rows, n_edges) | None}``."""
-        res = {}
-        for name, arr in self.visit_schedule_arrays(first_phase_work).items():
-            if arr is None:
-                res[name] = None
-                continue
-            sro32, c, e, out_rows = arr
-            self._keep.append(arr)
-            res[name] = (self._make_view(sro32, c, e, n_rows=int(out_rows.numel())), out_rows, int(c.numel()))
-        return res
-
-    def visit_schedule_arrays(self, first_phase_work: float):
-        """Split my rows so that as few as possible are visited twice.
-
-        Rows without a remote neighbour (Z) never wait for the exchange.  Of the rows WITH one (H), a prefix A (in row
-        order) is summed over its own-source edges while the exchange is in flight and gets its halo-source edges in a
-        second visit; the rest B = H minus A is summed ONCE, over all its edges, after the halo has landed.  A is made just
-        large enough that phase 1 (Z in full + A's own-source edges) fills ``first_phase_work`` (in units of
-        ``edges + 4 * rows``, the work model of ``cost_balanced_bounds``): at 8 ranks the exchange outlasts the whole
-        own-source pass and A = H (the plain two-pass form); at 2 ranks Z alone nearly covers the exchange and B = H.
-
-        Returns ``dict(first=…, second_all=… | None, second_halo=… | None)`` of ``(row_offset, cols, eids, out_rows)`` sub-CSRs
-        (view row ``i`` is local row ``out_rows[i]``); ``second_all`` uses the unified column space ``[own rows | halo rows]``
-        (``stg_agg_packed_sum_rows2_f32``), ``first`` own-row columns, ``second_halo`` halo-buffer columns.
-        """
-        dev = self.local_row_offset.device
-        n = self.n_rows
-        odeg = (self.own_ro[1:] - self.own_ro[:-1]).to(torch.int64)
-        hdeg = (self.halo_ro[1:] - self.halo_ro[:-1]).to(torch.int64)
-        has_halo = hdeg > 0
-        work_z = float((odeg[~has_halo] + 4).sum())
-        w_h = torch.where(has_halo, odeg + 4, torch.zeros_like(odeg))
-        cum = torch.cumsum(w_h, 0)
-        need = max(first_phase_work - work_z, 0.0)
-        total_h = float(cum[-1]) if n else 0.0
-        if need >= total_h:
-            cut = n                                   # A = H
-        elif need <= 0:
-            cut = 0                                   # A empty
-        else:
-            cut = int(torch.searchsorted(cum, torch.tensor([need], dtype=cum.dtype, device=dev))[0]) + 1
-        idx = torch.arange(n, device=dev)
-        in_a = has_halo & (idx < cut)
-        in_b = has_halo & ~in_a
-        self.schedule_stats = {"rows": n, "rows_no_halo": int((~has_halo).sum()), "rows_two_visits": int(in_a.sum()),
-                               "rows_one_visit_after_halo": int(in_b.sum())}
-
-        def subset(ro, cols, eids, sel):
-            ro64 = ro.to(torch.int64)
-            beg, deg = ro64[sel], (ro64[sel + 1] - ro64[sel])
-            sro = torch.zeros(sel.numel() + 1, dtype=torch.int64, device=dev)
-            sro[1:] = torch.cumsum(deg, 0)
-            pos = torch.repeat_interleave(beg - sro[:-1], deg) + torch.arange(int(sro[-1]), device=dev)
-            out_rows = sel.to(torch.int32).contiguous()
-            return sro.to(torch.int32).contiguous(), cols[pos].contiguous(), eids[pos].contiguous(), out_rows
-
-        res = {}
-        sel1 = torch.nonzero(~has_halo | in_a).reshape(-1)
-        res["first"] = subset(self.own_ro, self.own_cols, self.own_eids, sel1)
-        sel_b = torch.nonzero(in_b).reshape(-1)
-        res["second_all"] = subset(self.local_row_offset, self.local_cols, self.local_eids, sel_b) if sel_b.numel() else None
-        sel_a = torch.nonzero(in_a).reshape(-1)
-        res["second_halo"] = subset(self.halo_ro, self.halo_cols, self.halo_eids, sel_a) if sel_a.numel() else None
-        return res
-
     def new_halo_buffer(self, feat: int, like: torch.Tensor) -> torch.Tensor:
         return torch.empty(max(self.n_halo, 1), feat, dtype=like.dtype, device=like.device)[:self.n_halo]
 

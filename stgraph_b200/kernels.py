@@ -196,39 +196,6 @@ def agg_packed_sum_rows(view: _lib.StgCsrView, meta: torch.Tensor, out_rows, x: 
     return out
 
 
-def agg_packed_sum_rows2(view: _lib.StgCsrView, meta: torch.Tensor, out_rows, x: torch.Tensor, x2: torch.Tensor, split_col: int,
-                         row_scale, out: torch.Tensor, accumulate=False, stream=None) -> torch.Tensor:
-    """:func:`agg_packed_sum_rows` with two source matrices (``stg_agg_packed_sum_rows2_f32``): a packed column
-    ``c < split_col`` reads ``x[c]``, a column ``c >= split_col`` reads ``x2[c - split_col]``."""
-    global launch_count
-    _check(x, "x")
-    _check(x2, "x2")
-    _check(out, "out")
-    _check(meta, "meta", torch.int32)
-    feat = x.numel() // max(x.shape[0], 1)
-    if x2.numel() != x2.shape[0] * feat or out.numel() != out.shape[0] * feat:
-        raise ValueError("x, x2 and out must have the same row width")
-    if meta.numel() < 2 * view.num_edges:
-        raise ValueError(f"meta has {meta.numel() // 2} entries for {view.num_edges} edges")
-    if out_rows is not None:
-        _check(out_rows, "out_rows", torch.int32)
-        if out_rows.numel() != view.num_nodes:
-            raise ValueError("out_rows needs one entry per view row")
-    elif out.shape[0] != view.num_nodes:
-        raise ValueError(f"out has {out.shape[0]} rows for a view of {view.num_nodes} rows")
-    if row_scale is not None:
-        _check(row_scale, "row_scale")
-        if row_scale.numel() != out.shape[0]:
-            raise ValueError(f"row_scale must have one entry per row of out ({out.shape[0]}), got {row_scale.numel()}")
-    if view.num_nodes == 0 or feat == 0:
-        return out
-    _lib.call("stg_agg_packed_sum_rows2_f32", ctypes.byref(view), meta.data_ptr(), _lib.ptr(out_rows), x.data_ptr(), x2.data_ptr(),
-              int(split_col), feat, _lib.ptr(row_scale), out.data_ptr(), {False: 0, True: 1, "red": 2}[accumulate],
-              stream if stream is not None else _lib.current_stream_ptr())
-    launch_count += 1 + (1 if view.hub_threshold > 0 else 0)
-    return out
-
-
 def agg_scaled_sum_graph(csr, x: torch.Tensor, nbr_scale=None, edge_scale=None, row_scale=None,
                          out: torch.Tensor | None = None) -> torch.Tensor:
     """:func:`agg_scaled_sum` over one direction of a graph object (``graph/static/csr.py:CSR``).  A static CSR
