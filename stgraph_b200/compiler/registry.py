@@ -15,6 +15,9 @@ stock ``GATConv`` gradients depend on it.
 """
 from __future__ import annotations
 
+import os
+import warnings
+
 import torch
 
 from .program import Stmt, Var
@@ -106,8 +109,22 @@ def _add_dydx(ctx, fstmt, pos, x, y):
     return [], 1
 
 
+#: STG_SUB_GRAD=correct gives the subtrahend its mathematical gradient (-1).  The default keeps the reference's rule
+#: (+1 for BOTH operands, ``registry.py:210-213``): stock GATConv's ``emb - max([emb])`` traces to ``Sub(V0, V0)`` and the
+#: reference's d_el / d_er -- pinned by tests/golden/ref_kernels.npz -- depend on it (SURVEY.md trap T2).
+SUB_GRAD_CORRECT = os.environ.get("STG_SUB_GRAD", "reference") == "correct"
+_warned_sub = []
+
+
 def _sub_dydx(ctx, fstmt, pos, x, y):
-    # reference rule: "y = x - k => dydx = 1" for BOTH operands (registry.py:210-213)
+    if pos == 1 and not is_const_scalar(fstmt.args[0]) and fstmt.args[0] != fstmt.args[1]:
+        if SUB_GRAD_CORRECT:
+            return [], -1
+        if not _warned_sub:
+            _warned_sub.append(True)
+            warnings.warn("vertex program computes a - b with b requiring a gradient: the reference's Sub rule passes +1 to "
+                          "BOTH operands (registry.py:210-213), so d_b has the wrong sign; set STG_SUB_GRAD=correct for -1",
+                          RuntimeWarning, stacklevel=2)
     return [], 1
 
 
