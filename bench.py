@@ -592,7 +592,7 @@ def main():
                 env = dict(os.environ, STG_CONFIGS_OUT=path, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
                 del x, gout, out_f, out_b
                 torch.cuda.empty_cache()
-                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py"), "1", "2", "3", "4"], env=env,
+                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py"), "1", "2", "3", "4", "ref"], env=env,
                                cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=420, check=True)
                 res = json.load(open(path))
             extras["other_configs"] = res

@@ -325,11 +325,87 @@ def config4(scale=1.0):
     out["config4_dynamic_tgcn"] = res
 
 
+# ------------------------------------------------------------------ the reference's own kernels on configs 1-3
+def reference_kernels():
+    """Kernel-only times of the CUDA the reference's code generator emits (``oracle/_ref/*_gpu.so``, built by
+    ``oracle/build_ref.py`` as compute_100 PTX like its JIT would), launched with its own geometry on the graphs of configs
+    1-3: what an epoch of the reference spends in its aggregation kernels, beside our epoch times above."""
+    import ctypes
+
+    from oracle import ref_emulate as RE
+
+    res = {}
+
+    def time_case(case, graph, feat_dims, n, e, reps=20):
+        so = os.path.join(RE.REF_DIR, case + "_gpu.so")
+        if not os.path.exists(so):
+            return None
+        kernels_meta, _ = RE.load_case(case)
+        lib = ctypes.CDLL(so)
+        F_, B_ = graph._forward_graph, graph._backward_graph
+        tensors, out_ms = {}, {}
+        stream = torch.cuda.current_stream().cuda_stream
+        for k in kernels_meta:
+            csr = F_ if k["parallel_mode"] == "DstParallel" else B_
+            for name, vt, shp in zip(k["args"], k["arg_types"], k["arg_shapes"]):
+                if name not in tensors:
+                    lead = e if vt == "EDGE" else n
+                    tensors[name] = (torch.zeros([lead] + shp, device=dev) if name in k["rets"]
+                                     else torch.rand([lead] + shp, device=dev) + 0.1)
+            arr = (ctypes.c_void_p * len(k["args"]))(*[ctypes.c_void_p(tensors[a].data_ptr()) for a in k["args"]])
+            md = k["max_dims"]
+            max_dims = [1, md[-1]] if len(md) == 1 else md
+            feat = 1
+            for d_ in md:
+                feat *= d_
+            nblks, nthrs, group, npb = RE.reference_launch_params(feat, n)
+            fn = getattr(lib, "launch_" + k["name"])
+            fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 7 + [ctypes.c_void_p]
+
+            def launch():
+                rc = fn(arr, csr.row_offset.data_ptr(), csr.eids.data_ptr(), csr.column_indices.data_ptr(),
+                        csr.node_ids.data_ptr(), n, max_dims[1], max_dims[0], group, npb, nblks, nthrs, stream)
+                assert rc == 0, rc
+
+            for _ in range(3):
+                launch()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                launch()
+            b.record()
+            torch.cuda.synchronize()
+            out_ms[k["name"] + "_" + k["direction"]] = a.elapsed_time(b) / reps
+        return out_ms
+
+    d = synthetic.cora_shaped(seed=0, device=dev)
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
+    t = time_case("gcn_f16", g, 16, d["num_nodes"], int(d["src"].shape[0]))
+    if t:
+        res["config1_gcn_f16_kernels_ms"] = t
+        res["config1_epoch_kernels_ms_estimate"] = 2 * sum(t.values())        # two layers (the F=7 layer timed as F=16)
+    d = synthetic.wikimaths_shaped(seed=0, device=dev)
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
+    t = time_case("gcn_f16", g, 16, d["num_nodes"], int(d["src"].shape[0]))
+    if t:
+        res["config2_gcn_f16_kernels_ms"] = t
+        res["config2_epoch_kernels_ms_estimate"] = 3 * 723 * sum(t.values())  # three convolutions per timestep, fwd + bwd
+    d = synthetic.arxiv_shaped(seed=0, device=dev)
+    g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
+    t = time_case("gat_h8d16", g, 128, d["num_nodes"], int(d["src"].shape[0]), reps=5)
+    if t:
+        res["config3_gat_h8d16_kernels_ms"] = t
+        res["config3_fwd_bwd_kernels_ms"] = sum(t.values())
+    if not res:
+        res["unavailable"] = "oracle/_ref/*_gpu.so not built (oracle/build_ref.py needs /root/reference)"
+    out["reference_kernels"] = res
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "3", "4"]
     for w in which:
         try:
-            {"1": config1, "2": config2, "3": config3, "4": config4}[w]()
+            {"1": config1, "2": config2, "3": config3, "4": config4, "ref": reference_kernels}[w]()
         except Exception as ex:
             import traceback
             traceback.print_exc()

@@ -741,6 +741,17 @@ inline int queue_chunk() {
   return v;
 }
 
+// Hub CTAs per SM (STG_HUB_GRID; read once).  Two 512-thread hub CTAs fill an SM's register file, so the row kernel
+// launched behind them as a programmatic dependent cannot become resident before they retire.
+inline int hub_grid_mult() {
+  static const int v = [] {
+    const char* e = getenv("STG_HUB_GRID");
+    const int c = e ? atoi(e) : 2;
+    return c < 1 ? 1 : (c > 4 ? 4 : c);
+  }();
+  return v;
+}
+
 template <int VEC, int GROUP, int NACC, int MODE>
 int launch_agg(const AggParams& p, cudaStream_t stream) {
   constexpr int rows_per_block = (kBlockThreads / 32) * (32 / GROUP);
@@ -752,7 +763,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
   const bool overlap = hubs && p.num_edges >= (1 << 18);
   if (hubs) {
-    agg_hub_kernel<VEC, GROUP, NACC, MODE><<<2 * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC, MODE><<<hub_grid_mult() * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
