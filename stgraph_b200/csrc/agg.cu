@@ -741,15 +741,17 @@ inline int queue_chunk() {
   return v;
 }
 
-// Hub CTAs per SM (STG_HUB_GRID; read once).  Two 512-thread hub CTAs fill an SM's register file, so the row kernel
-// launched behind them as a programmatic dependent cannot become resident before they retire.
-inline int hub_grid_mult() {
+// Hub CTAs per SM (STG_HUB_GRID overrides; read once).  Two 512-thread hub CTAs fill an SM's register file, so the row
+// kernel launched behind them as a programmatic dependent cannot become resident before they retire: on a large graph
+// one hub CTA per SM leaves half of every SM to the row kernel from the start (config 5 forward / backward 2.139 /
+// 2.211 ms against 2.161 / 2.302 ms); small launches keep two (the hub rows are their critical path).
+inline int hub_grid_mult(int num_edges) {
   static const int v = [] {
     const char* e = getenv("STG_HUB_GRID");
-    const int c = e ? atoi(e) : 2;
-    return c < 1 ? 1 : (c > 4 ? 4 : c);
+    const int c = e ? atoi(e) : 0;
+    return c < 0 ? 0 : (c > 4 ? 4 : c);
   }();
-  return v;
+  return v > 0 ? v : (num_edges >= (1 << 24) ? 1 : 2);
 }
 
 template <int VEC, int GROUP, int NACC, int MODE>
@@ -763,7 +765,7 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   // graph (config 2, 1446 aggregations per epoch: 190 ms against 158 ms), so they keep plain stream order.
   const bool overlap = hubs && p.num_edges >= (1 << 18);
   if (hubs) {
-    agg_hub_kernel<VEC, GROUP, NACC, MODE><<<hub_grid_mult() * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
+    agg_hub_kernel<VEC, GROUP, NACC, MODE><<<hub_grid_mult(p.num_edges) * (sm_count() / kHubCluster) * kHubCluster, kHubThreads, 0, stream>>>(p);
     STG_LAUNCH_CHECK("agg_hub_kernel");
   }
   if (blocks > 0) {
