@@ -112,25 +112,23 @@ template <int NACC> struct UnrollFor { static constexpr int value = NACC >= 4 ? 
 // the backward passes carry four per-edge scalars next to each neighbour row: 8 in flight would cost occupancy
 template <int NACC> struct UnrollBwd { static constexpr int value = NACC >= 4 ? 2 : 4; };
 
-// Calls body(integral_constant<G>, j) over [0, n) with G = U for every full group and exact powers of two for the tail.
+// Calls body(integral_constant<G>, j) over [0, n) with G = U for every full group and ONE exactly-sized group for the
+// tail: a row of 7 edges is one batch of 7 loads (one L2 round trip), not 4 + 2 + 1 (three dependent ones).
 template <int U, class Body>
 __device__ __forceinline__ void for_exact_groups(int n, Body&& body) {
   int j = 0;
   for (; j + U <= n; j += U) body(std::integral_constant<int, U>{}, j);
-  if constexpr (U >= 8) {
-    if (j + 4 <= n) {
-      body(std::integral_constant<int, 4>{}, j);
-      j += 4;
-    }
-  }
-  if constexpr (U >= 4) {
-    if (j + 2 <= n) {
-      body(std::integral_constant<int, 2>{}, j);
-      j += 2;
-    }
-  }
   if constexpr (U >= 2) {
-    if (j < n) body(std::integral_constant<int, 1>{}, j);
+    switch (n - j) {
+      case 1: body(std::integral_constant<int, 1>{}, j); break;
+      case 2: if constexpr (U > 2) body(std::integral_constant<int, 2>{}, j); break;
+      case 3: if constexpr (U > 3) body(std::integral_constant<int, 3>{}, j); break;
+      case 4: if constexpr (U > 4) body(std::integral_constant<int, 4>{}, j); break;
+      case 5: if constexpr (U > 5) body(std::integral_constant<int, 5>{}, j); break;
+      case 6: if constexpr (U > 6) body(std::integral_constant<int, 6>{}, j); break;
+      case 7: if constexpr (U > 7) body(std::integral_constant<int, 7>{}, j); break;
+      default: break;
+    }
   }
 }
 
