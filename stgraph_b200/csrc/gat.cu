@@ -662,13 +662,24 @@ inline int gat_queue_chunk() {
   return v;
 }
 
+// Hub CTAs per SM (STG_GAT_HUB_GRID; read once): four fill the register file until they exit, fewer leave room for the
+// row kernel from the start but serve fewer hub rows at a time.
+inline int gat_hub_grid_mult() {
+  static const int v = [] {
+    const char* e = getenv("STG_GAT_HUB_GRID");
+    const int c = e ? atoi(e) : 4;
+    return c < 1 ? 1 : (c > 8 ? 8 : c);
+  }();
+  return v;
+}
+
 template <int VEC, int GROUP, int NACC>
 int launch_gat(const GatParams& p, int which, cudaStream_t s) {
   const int rows_per_block = (kGatThreads / 32) * (32 / GROUP);
   const int blocks = (p.num_rows + rows_per_block - 1) / rows_per_block;
   if (blocks <= 0) return STG_OK;
   const bool hubs = p.hub_threshold > 0 && p.hub_rows != nullptr;
-  const int hub_grid = 4 * (sm_count() / kGatCluster) * kGatCluster;   // 8-warp CTAs, <= 64 registers: 4 per SM leave half an SM to the row kernel
+  const int hub_grid = gat_hub_grid_mult() * (sm_count() / kGatCluster) * kGatCluster;   // 8-warp CTAs of <= 64 registers per SM
   // Hub rows first: the longest rows are the critical path, the row kernel fills the SMs they leave idle.
   if (hubs) {
     constexpr int ht = HubThreads<NACC>::value;
