@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 2
+#define STG_ABI_VERSION 3
 
 typedef enum StgStatus {
   STG_OK = 0,
@@ -321,6 +321,16 @@ int stg_gru_reset_bwd_f32(const float* pr, const float* h, const float* d_hr, fl
 int stg_gru_update_fwd_f32(const float* pz, const float* ph, const float* h, float* out, int64_t n, void* stream);
 int stg_gru_update_bwd_f32(const float* pz, const float* ph, const float* h, const float* d_out, float* d_pz,
                            float* d_ph, float* d_h, int64_t n, void* stream);
+/* The same gate arithmetic on the block layout of the one-Function cell (stgraph_b200/ops_tgcn.py): p and d_p are
+ * [rows, 3*hid] row-major holding the gate pre-activations as column blocks (z | r | h); h, hr, out, d_out, d_hr, d_h are
+ * [rows, hid].  update_bwd writes the z and h blocks of d_p and d_h = d_out * z; reset_bwd writes the r block of d_p and
+ * ADDS d_hr * r to d_h (call it after update_bwd). */
+int stg_tgcn_reset_fwd_f32(const float* p, const float* h, float* hr, int64_t rows, int32_t hid, void* stream);
+int stg_tgcn_reset_bwd_f32(const float* p, const float* h, const float* d_hr, float* d_p, float* d_h, int64_t rows,
+                           int32_t hid, void* stream);
+int stg_tgcn_update_fwd_f32(const float* p, const float* h, float* out, int64_t rows, int32_t hid, void* stream);
+int stg_tgcn_update_bwd_f32(const float* p, const float* h, const float* d_out, float* d_p, float* d_h, int64_t rows,
+                            int32_t hid, void* stream);
 
 /* Workspace needed by stg_csr_build for E edges / N nodes. */
 size_t stg_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes);

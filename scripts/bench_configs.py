@@ -95,7 +95,7 @@ def config2():
     w = d["edge_weight"].reshape(-1, 1).contiguous()
     targets = d["targets"]
     res = {}
-    for name, fused in (("dropin", False), ("default", None), ("fused", True)):
+    for name, fused in (("dropin", False), ("default", None), ("fused", True), ("fused_pieces", "pieces")):
         torch.manual_seed(0)
         model = STGraphTGCN(lags, 16, 1, fused).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-2)

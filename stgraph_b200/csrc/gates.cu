@@ -91,10 +91,111 @@ __global__ void __launch_bounds__(kGateThreads) update_bwd_kernel(const float* _
   }
 }
 
+// ---- the same gate arithmetic on the block layout of the one-Function cell (ops_tgcn.py): the three gate
+// pre-activations are the column blocks (z | r | h) of ONE [rows, 3*hid] matrix p, so that every GEMM that produces or
+// consumes them works on a column block in place and the bias / weight gradients are one reduction / one GEMM each.
+__global__ void __launch_bounds__(kGateThreads) cell_reset_fwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
+                                                                     float* __restrict__ hr, int64_t n, int hid) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / hid;
+    const int j = static_cast<int>(i - r * hid);
+    hr[i] = h[i] * sigmoidf_(p[r * 3 * hid + hid + j]);
+  }
+}
+
+// d_p[:, r block] = d_hr * h * r * (1 - r);  d_h += d_hr * r   (d_h already holds the update gate's share)
+__global__ void __launch_bounds__(kGateThreads) cell_reset_bwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
+                                                                     const float* __restrict__ d_hr, float* __restrict__ d_p,
+                                                                     float* __restrict__ d_h, int64_t n, int hid) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / hid;
+    const int j = static_cast<int>(i - r * hid);
+    const int64_t q = r * 3 * hid + hid + j;
+    const float s = sigmoidf_(p[q]);
+    const float g = d_hr[i];
+    d_p[q] = g * h[i] * s * (1.f - s);
+    d_h[i] += g * s;
+  }
+}
+
+__global__ void __launch_bounds__(kGateThreads) cell_update_fwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
+                                                                      float* __restrict__ out, int64_t n, int hid) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / hid;
+    const int j = static_cast<int>(i - r * hid);
+    const int64_t q = r * 3 * hid + j;
+    const float z = sigmoidf_(p[q]);
+    out[i] = z * h[i] + (1.f - z) * tanhf(p[q + 2 * hid]);
+  }
+}
+
+// d_p[:, z block], d_p[:, h block] and d_h = d_out * z (the reset gate's share is added by cell_reset_bwd_kernel)
+__global__ void __launch_bounds__(kGateThreads) cell_update_bwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
+                                                                      const float* __restrict__ d_out, float* __restrict__ d_p,
+                                                                      float* __restrict__ d_h, int64_t n, int hid) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / hid;
+    const int j = static_cast<int>(i - r * hid);
+    const int64_t q = r * 3 * hid + j;
+    const float z = sigmoidf_(p[q]);
+    const float t = tanhf(p[q + 2 * hid]);
+    const float g = d_out[i];
+    d_p[q] = g * (h[i] - t) * z * (1.f - z);
+    d_p[q + 2 * hid] = g * (1.f - z) * (1.f - t * t);
+    d_h[i] = g * z;
+  }
+}
+
 }  // namespace
 }  // namespace stg
 
 using namespace stg;
+
+STG_API int stg_tgcn_reset_fwd_f32(const float* p, const float* h, float* hr, int64_t rows, int32_t hid, void* stream) {
+  STG_CHECK_ARG(rows >= 0 && hid > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), hid);
+  if (rows == 0) return STG_OK;
+  STG_CHECK_ARG(p && h && hr, "NULL tensor");
+  const int64_t n = rows * hid;
+  cell_reset_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, hr, n, hid);
+  STG_LAUNCH_CHECK("cell_reset_fwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_tgcn_reset_bwd_f32(const float* p, const float* h, const float* d_hr, float* d_p, float* d_h, int64_t rows,
+                                   int32_t hid, void* stream) {
+  STG_CHECK_ARG(rows >= 0 && hid > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), hid);
+  if (rows == 0) return STG_OK;
+  STG_CHECK_ARG(p && h && d_hr && d_p && d_h, "NULL tensor");
+  const int64_t n = rows * hid;
+  cell_reset_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_hr, d_p, d_h, n, hid);
+  STG_LAUNCH_CHECK("cell_reset_bwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_tgcn_update_fwd_f32(const float* p, const float* h, float* out, int64_t rows, int32_t hid, void* stream) {
+  STG_CHECK_ARG(rows >= 0 && hid > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), hid);
+  if (rows == 0) return STG_OK;
+  STG_CHECK_ARG(p && h && out, "NULL tensor");
+  const int64_t n = rows * hid;
+  cell_update_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, out, n, hid);
+  STG_LAUNCH_CHECK("cell_update_fwd_kernel");
+  return STG_OK;
+}
+
+STG_API int stg_tgcn_update_bwd_f32(const float* p, const float* h, const float* d_out, float* d_p, float* d_h, int64_t rows,
+                                    int32_t hid, void* stream) {
+  STG_CHECK_ARG(rows >= 0 && hid > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), hid);
+  if (rows == 0) return STG_OK;
+  STG_CHECK_ARG(p && h && d_out && d_p && d_h, "NULL tensor");
+  const int64_t n = rows * hid;
+  cell_update_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_out, d_p, d_h, n, hid);
+  STG_LAUNCH_CHECK("cell_update_bwd_kernel");
+  return STG_OK;
+}
 
 STG_API int stg_bias_clamp_f32(float* a, const float* bias, int64_t rows, int32_t cols, float lo, float hi, void* stream) {
   STG_CHECK_ARG(rows >= 0 && cols > 0, "bad shape (%lld x %d)", static_cast<long long>(rows), cols);

@@ -5,13 +5,14 @@ Three ``GCNConv`` + three ``Linear(2H, H)`` GRU gates; module names (``conv_z/r/
 clamped to +-1e6 exactly like the reference.
 
 ``fused=True`` keeps the parameters and the math but runs the three graph convolutions as ONE
-GEMM ``X @ [W_z | W_r | W_h]`` and ONE aggregation of width 3H through ``ops_gcn.gcn_aggregate``
-(every output column of a GEMM / of the aggregation is computed independently, so the values
-are the same as three separate convolutions up to cuBLAS tiling), the gates as GEMMs on column
-blocks (no concatenations) and the element-wise work as three fused passes (``ops_gru``: bias +
-clamp, reset gate, update gate + candidate state) instead of ~16 torch kernels, with no tracing or
-executor work per step; a whole BPTT window can be captured in a CUDA graph (SURVEY.md section
-8(f).1).
+GEMM ``X @ [W_z | W_r | W_h]`` and ONE aggregation of width 3H (every output column of a GEMM / of
+the aggregation is computed independently, so the values are the same as three separate
+convolutions up to cuBLAS tiling), the gates as GEMMs on column blocks (no concatenations) and the
+element-wise work as three fused passes (bias + clamp, reset gate, update gate + candidate state)
+instead of ~16 torch kernels, with no tracing or executor work per step; a whole BPTT window can
+be captured in a CUDA graph.  The whole cell is one autograd op with a
+hand-written backward (``ops_tgcn``); ``fused="pieces"`` chains the same kernels through torch
+autograd piece by piece (``ops_gcn`` / ``ops_gru``), which costs about three times the launches.
 """
 import torch
 
@@ -19,7 +20,7 @@ from ..static.gcn_conv import GCNConv
 
 
 class TGCN(torch.nn.Module):
-    def __init__(self, in_channels, out_channels, fused: bool | None = None):
+    def __init__(self, in_channels, out_channels, fused: bool | str | None = None):
         """``fused=None`` (default): run the fused cell whenever it computes the same thing as the three separate
         convolutions (always, for the cell as the reference builds it: the convolutions share the graph, ``X`` and
         ``norm``); ``fused=False`` forces the reference-structured path (three traced vertex programs through the
@@ -64,9 +65,7 @@ class TGCN(torch.nn.Module):
     def _calculate_hidden_state(self, Z, H, H_tilde):
         return Z * H + (1 - Z) * H_tilde
 
-    def _forward_fused(self, g, X, edge_weight, H):
-        from ....ops_gcn import gcn_aggregate
-
+    def _check_fused_inputs(self, g, edge_weight):
         from ....utils.constants import SizeConstants
 
         norm = g.get_ndata("norm")
@@ -77,8 +76,40 @@ class TGCN(torch.nn.Module):
             raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_nodes, 1)")
         if norm.requires_grad or (edge_weight is not None and edge_weight.requires_grad):
             raise RuntimeError("the fused TGCN cell gives no gradient for 'norm' / edge_weight; use TGCN(fused=False)")
+        return norm
+
+    def _packed_parameters(self):
+        """The cell's parameters in the layout of ``ops_tgcn`` (``[W_z|W_r|W_h]`` ...), packed with differentiable torch
+        ops ONCE per BPTT window instead of once per time step: the pack is reused until a parameter changes (in-place
+        version counter, storage) or a backward pass has run through it (a hook on the packed weight marks it stale)."""
+        from ....ops_tgcn import pack_parameters
+
+        mods = (self.conv_z, self.conv_r, self.conv_h, self.linear_z, self.linear_r, self.linear_h)
+        params = [t for m in mods for t in (m.weight, m.bias)]
+        key = (torch.is_grad_enabled(),) + tuple((id(t), t._version, t.data_ptr(), t.requires_grad) for t in params)
+        cache = self.__dict__.get("_pack_cache")
+        if cache is not None and cache[0] == key and not cache[2][0]:
+            return cache[1]
+        packed = pack_parameters(*mods)
+        stale = [False]
+        if packed[0].requires_grad:
+            packed[0].register_hook(lambda grad, flag=stale: flag.__setitem__(0, True))
+        self.__dict__["_pack_cache"] = (key, packed, stale)
+        return packed
+
+    def _forward_fused(self, g, X, edge_weight, H):
+        """The cell as ONE autograd op with a hand-written backward (``ops_tgcn``)."""
+        from ....ops_tgcn import tgcn_cell
+
+        norm = self._check_fused_inputs(g, edge_weight)
+        return tgcn_cell(g, X, H, norm, edge_weight, self._packed_parameters())
+
+    def _forward_fused_pieces(self, g, X, edge_weight, H):
+        """The fused cell of round 1 (``fused="pieces"``): the same kernels, chained by torch autograd piece by piece."""
+        from ....ops_gcn import gcn_aggregate
         from ....ops_gru import bias_clamp, gru_reset, gru_update
 
+        norm = self._check_fused_inputs(g, edge_weight)
         hid = self.out_channels
         W = torch.cat((self.conv_z.weight, self.conv_r.weight, self.conv_h.weight), dim=1)
         b = torch.cat((self.conv_z.bias, self.conv_r.bias, self.conv_h.bias))
@@ -105,6 +136,8 @@ class TGCN(torch.nn.Module):
         if self.fused or (self.fused is None and self._can_fuse(g, edge_weight)):
             if H is None:      # allocated on the device directly: no H2D copy, CUDA-graph capturable
                 H = torch.zeros(X.shape[0], self.out_channels, device=X.device, dtype=X.dtype)
+            if self.fused == "pieces":
+                return self._forward_fused_pieces(g, X, edge_weight, H)
             return self._forward_fused(g, X, edge_weight, H)
         H = self._set_hidden_state(X, H)
         Z = self._calculate_update_gate(g, X, edge_weight, H)

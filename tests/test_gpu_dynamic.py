@@ -194,3 +194,32 @@ def test_bptt_over_snapshots_through_state_stack(cuda, kind):
     G.reset_graph()
     G.get_graph(0)
     assert G.current_timestamp == 0 and not G._is_backprop_state
+
+
+@pytest.mark.parametrize("kind", ["naive", "pcsr", "gpma"])
+def test_tgcn_one_op_cell_on_dynamic_snapshots(cuda, kind):
+    """The one-op TGCN cell on snapshots: the views are captured at forward time (no rewind in backward); values and
+    gradients equal the reference-structured cell on a NaiveGraph of the same snapshots."""
+    from stgraph_b200.graph import NaiveGraph
+    from stgraph_b200.nn.pytorch import TGCN
+
+    n, T = 120, 4
+    snaps = _stream(n, T, base=900, churn=150, seed=4, dup=False)
+    torch.manual_seed(5)
+    cells = [TGCN(8, 16, fused=f).to(cuda) for f in (False, None)]
+    cells[1].load_state_dict(cells[0].state_dict())
+    xs = [torch.randn(n, 8, device=cuda) for _ in range(T)]
+    res = []
+    for cell, G in zip(cells, (NaiveGraph(snaps, n), _classes()[kind](snaps, n))):
+        H, cost = None, 0
+        for t, x in enumerate(xs):
+            G.get_graph(t)
+            G.set_ndata("norm", G.degree_norm())
+            H = cell(G, x, None, H)
+            cost = cost + (H ** 2).mean()
+        cost.backward()
+        res.append((H.detach(), {k: p.grad.clone() for k, p in cell.named_parameters()}))
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-5, atol=1e-6)
+    for k in res[0][1]:
+        ga, gb = res[0][1][k], res[1][1][k]
+        assert (ga - gb).abs().max() <= 2e-5 * ga.abs().max() + 1e-7, k

@@ -190,9 +190,10 @@ def test_gat_units_match_ir_interpreter(cuda):
     assert set(v.id for v in ex.grad_out) == {"Velinb", "Vercen", "Vfeat_srcinb"}
 
 
-@pytest.mark.parametrize("fused", [None, False])
+@pytest.mark.parametrize("fused", [None, "pieces", False])
 def test_tgcn_cell_matches_torch(cuda, fused):
-    """Default construction (the fused cell is picked automatically) and the reference-structured path."""
+    """Default construction (the one-op fused cell is picked automatically), the piecewise fused cell and the
+    reference-structured path."""
     from stgraph_b200.nn.pytorch import TGCN
 
     n, e = 200, 2000
@@ -291,7 +292,8 @@ def test_fused_edge_softmax_rejects_unsupported_dim(cuda):
         gat_edge_softmax_aggregate(g, el, el, feat)
 
 
-def test_tgcn_fused_cell_equals_reference_structure(cuda):
+@pytest.mark.parametrize("mode", [True, "pieces"])
+def test_tgcn_fused_cell_equals_reference_structure(cuda, mode):
     """fused=True (one GEMM + one aggregation of width 3H) gives the same values and gradients."""
     from stgraph_b200.nn.pytorch import TGCN
 
@@ -300,7 +302,7 @@ def test_tgcn_fused_cell_equals_reference_structure(cuda):
     g.set_ndata("norm", g.degree_norm())
     torch.manual_seed(7)
     a = TGCN(8, 16, fused=False).to(cuda)
-    b = TGCN(8, 16, fused=True).to(cuda)
+    b = TGCN(8, 16, fused=mode).to(cuda)
     b.load_state_dict(a.state_dict())
     w = torch.rand(e, 1, device=cuda) + 0.1
     xs = [torch.randn(n, 8, device=cuda) for _ in range(5)]
@@ -497,3 +499,77 @@ def test_fused_clamp_propagates_nan_like_torch(cuda):
     a3 = a.clone().requires_grad_(True)
     torch.clamp(a3 * 1.0, -1e6, 1e6).backward(torch.ones_like(a3))
     assert torch.equal(a2.grad, a3.grad)            # torch's mask: no gradient where the value is NaN or clamped
+
+
+def _tgcn_pair(cuda, n=260, e=3000, seed=21):
+    from stgraph_b200.nn.pytorch import TGCN
+
+    g, src, dst = _graph(n, e, seed, cuda)
+    g.set_ndata("norm", g.degree_norm())
+    torch.manual_seed(seed)
+    a = TGCN(8, 16, fused=False).to(cuda)
+    b = TGCN(8, 16).to(cuda)
+    b.load_state_dict(a.state_dict())
+    w = torch.rand(e, 1, device=cuda) + 0.1
+    return g, a, b, w
+
+
+def _window(cell, g, xs, w, H=None):
+    cost = 0
+    for x in xs:
+        H = cell(g, x, w, H)
+        cost = cost + (H ** 2).mean()
+    return cost, H
+
+
+def test_tgcn_packed_parameters_follow_optimizer_steps_and_repeated_backwards(cuda):
+    """The one-op cell packs its parameters once per BPTT window: the pack must be rebuilt after an optimizer step
+    (in-place parameter update) and after a backward pass (gradient accumulation over two windows without a step)."""
+    g, a, b, w = _tgcn_pair(cuda)
+    xs = [torch.randn(260, 8, device=cuda) for _ in range(6)]
+    opts = [torch.optim.SGD(m.parameters(), lr=0.05) for m in (a, b)]
+    for cell, opt in zip((a, b), opts):
+        # window 1 -> step; windows 2 and 3 accumulate into .grad without a step in between (truncated BPTT, H detached)
+        cost, H = _window(cell, g, xs[:2], w)
+        opt.zero_grad()
+        cost.backward()
+        opt.step()
+        opt.zero_grad()
+        cost, H = _window(cell, g, xs[2:4], w, H.detach())
+        cost.backward()
+        cost, H = _window(cell, g, xs[4:], w, H.detach())
+        cost.backward()
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert (pa - pb).abs().max() <= 1e-5 * pa.abs().max() + 1e-7, k
+        assert (pa.grad - pb.grad).abs().max() <= 2e-5 * pa.grad.abs().max() + 1e-7, k
+    # the pack is reused inside a window and dropped once a backward has run through it
+    b.zero_grad()
+    cost, _ = _window(b, g, xs[:3], w)
+    first = b._pack_cache[1][0]
+    assert b._packed_parameters()[0] is first
+    cost.backward()
+    assert b._packed_parameters()[0] is not first
+
+
+def test_tgcn_one_op_cell_input_gradient_and_no_grad(cuda):
+    """d/dX and d/dH of the one-op cell against the piecewise fused cell; inference under no_grad."""
+    from stgraph_b200.nn.pytorch import TGCN
+
+    g, a, b, w = _tgcn_pair(cuda, seed=33)
+    c = TGCN(8, 16, fused="pieces").to(cuda)
+    c.load_state_dict(b.state_dict())
+    x0 = torch.randn(260, 8, device=cuda)
+    h0 = torch.randn(260, 16, device=cuda)
+    grads = []
+    for cell in (b, c):
+        x, h = x0.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+        out = cell(g, x, w, h)
+        (out * torch.linspace(-1, 1, 16, device=cuda)).sum().backward()
+        grads.append((out.detach(), x.grad, h.grad))
+    torch.testing.assert_close(grads[0][0], grads[1][0], rtol=1e-5, atol=1e-6)
+    for u, v in zip(grads[0][1:], grads[1][1:]):
+        assert (u - v).abs().max() <= 1e-5 * v.abs().max() + 1e-7
+    with torch.no_grad():
+        out = b(g, x0, w, h0)
+    assert not out.requires_grad
+    torch.testing.assert_close(out, grads[0][0], rtol=1e-6, atol=1e-7)
