@@ -175,6 +175,14 @@ def config2():
         ours = [e for e in evs if "stg" in e.name or "agg_" in e.name or "gru_" in e.name or "bias_clamp" in e.name or "clamp_bwd" in e.name]
         res["our_kernels_per_timestep"] = len(ours) / steps
         res["our_kernel_durations_ms"] = sum(e.device_time for e in ours) / 1e3
+        hist = {}
+        for e in evs:
+            k = e.name.split("<")[0].split("(")[0].replace("void ", "").replace("at::native::", "")[:60]
+            c = hist.setdefault(k, [0, 0.0])
+            c[0] += 1
+            c[1] += e.device_time
+        res["kernel_histogram_per_timestep"] = {k: [round(c[0] / steps, 2), round(c[1] / c[0], 2)] for k, c in
+                                                sorted(hist.items(), key=lambda kv: -kv[1][0])[:24]}      # name -> [launches per step, mean us]
     except Exception as ex:
         res["kernel_profile_error"] = repr(ex)[:200]
     out["config2_tgcn_wikimaths_epoch_ms"] = res
