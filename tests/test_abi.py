@@ -38,7 +38,7 @@ def test_load_and_version():
 
 def test_struct_layouts_match_header():
     # sizes implied by the C declarations (LP64)
-    assert ctypes.sizeof(_lib.StgCsrView) == 4 * 8 + 4 * 4 + 2 * 8 + 2 * 4 + 8   # + work_queue (ABI 2)
+    assert ctypes.sizeof(_lib.StgCsrView) == 4 * 8 + 4 * 4 + 2 * 8 + 2 * 4 + 8   # + work_queue (since ABI 2)
     assert ctypes.sizeof(_lib.StgVmInstr) == 16
     assert ctypes.sizeof(_lib.StgVmTensor) == 16
     assert ctypes.sizeof(_lib.StgVmProgram) == 8 * 4 + 8 * _lib.VM_MAX_ACC + 16 * _lib.VM_MAX_TENSORS + 16 * _lib.VM_MAX_INSTR
