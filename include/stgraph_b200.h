@@ -332,6 +332,16 @@ int stg_tgcn_update_fwd_f32(const float* p, const float* h, float* out, int64_t 
 int stg_tgcn_update_bwd_f32(const float* p, const float* h, const float* d_out, float* d_p, float* d_h, int64_t rows,
                             int32_t hid, void* stream);
 
+/* Weight-gradient GEMM of the cell: C[K, Nc] = A[M, K]^T * B[M, Nc] in exact fp32 for M >> K, Nc (what torch autograd
+ * computes with cuBLAS for the gradients of conv_*.weight and linear_*.weight, tgcn.py:16-47), and, if colsum_b is not
+ * NULL, colsum_b[Nc] = column sums of B (the bias gradient).  A and B are row-major with leading dimensions lda >= K,
+ * ldb >= Nc (column blocks of wider matrices are fine); C is contiguous.  The M rows are split into slabs whose partial
+ * results are summed in slab order (deterministic); workspace: stg_gemm_tn_workspace_bytes(M, K, Nc) bytes (0 for small
+ * M: pass NULL). */
+size_t stg_gemm_tn_workspace_bytes(int64_t M, int32_t K, int32_t Nc);
+int stg_gemm_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t K, int32_t Nc, float* C,
+                    float* colsum_b, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Workspace needed by stg_csr_build for E edges / N nodes. */
 size_t stg_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes);
 

@@ -132,6 +132,9 @@ _SIGNATURES = {
     "stg_tgcn_reset_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p], True),
     "stg_tgcn_update_fwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p], True),
     "stg_tgcn_update_bwd_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p], True),
+    "stg_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32], False),
+    "stg_gemm_tn_f32": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p], True),
     "stg_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int32], False),
     "stg_csr_build": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32] + [c_void_p] * 12
                       + [c_void_p, c_size_t, c_void_p], True),

@@ -207,6 +207,33 @@ def agg_scaled_sum_graph(csr, x: torch.Tensor, nbr_scale=None, edge_scale=None, 
     return agg_packed_sum(csr.view(), meta, x, row_scale, out=out)
 
 
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, colsum: bool = False, out: torch.Tensor | None = None):
+    """``a^T @ b`` for ``a [M, K]``, ``b [M, Nc]`` with ``M >> K, Nc`` (``stg_gemm_tn_f32``: the weight-gradient GEMM of the
+    TGCN cell, exact fp32, deterministic); with ``colsum`` also the column sums of ``b`` (the bias gradient).  ``a`` and
+    ``b`` may be column blocks of wider row-major matrices (unit stride along the row)."""
+    global launch_count
+    for nm, t in (("a", a), ("b", b)):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+            raise TypeError(f"{nm} must be a 2-D float32 CUDA tensor")
+        if t.shape[1] > 1 and t.stride(1) != 1:
+            raise ValueError(f"{nm} must have unit stride along its rows (got strides {tuple(t.stride())})")
+    if a.shape[0] != b.shape[0]:
+        raise ValueError(f"a and b must have the same number of rows ({a.shape[0]} vs {b.shape[0]})")
+    m, k, nc = a.shape[0], a.shape[1], b.shape[1]
+    lda = a.stride(0) if m > 1 else max(k, 1)
+    ldb = b.stride(0) if m > 1 else max(nc, 1)
+    if out is not None and (out.shape != (k, nc) or not out.is_contiguous() or out.dtype != torch.float32):
+        raise ValueError(f"out must be a contiguous float32 [{k}, {nc}] tensor")
+    c = out if out is not None else torch.empty(k, nc, device=a.device, dtype=torch.float32)
+    cs = torch.empty(nc, device=a.device, dtype=torch.float32) if colsum else None
+    need = _lib.call("stg_gemm_tn_workspace_bytes", m, k, nc)
+    ws = torch.empty(need // 4, device=a.device, dtype=torch.float32) if need else None
+    _lib.call("stg_gemm_tn_f32", a.data_ptr(), lda, b.data_ptr(), ldb, m, k, nc, c.data_ptr(), _lib.ptr(cs), _lib.ptr(ws), need,
+              _lib.current_stream_ptr())
+    launch_count += 2 if need else 1
+    return (c, cs) if colsum else c
+
+
 def agg_scaled_sum_host(view: _lib.StgCsrView, x_host: torch.Tensor, out_host: torch.Tensor, scratch: torch.Tensor,
                         nbr_scale_host=None, edge_scale_host=None, row_scale_host=None, stream=None):
     """Host-buffer variant (H2D + kernel + D2H inside one C call); buffers should be pinned.

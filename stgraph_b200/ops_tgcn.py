@@ -30,6 +30,7 @@ import torch
 from . import _lib, kernels
 
 CLAMP = 1e6     # tgcn.py:23,31,39
+TALL_ROWS = 32768     # vertices from which the weight gradients go through kernels.gemm_tn instead of cuBLAS
 
 
 def pack_parameters(conv_z, conv_r, conv_h, linear_z, linear_r, linear_h):
@@ -100,21 +101,36 @@ class _TgcnCell(torch.autograd.Function):
         _lib.call("stg_clamp_bwd_f32", h.data_ptr(), dh.data_ptr(), dh.data_ptr(), dh.numel(), -CLAMP, CLAMP, st)
         kernels.launch_count += 3
         d_b3 = dh.sum(0) if need[8] else None
+        # weight gradients: [K, N] x [N, Nc] with N = number of vertices.  On large graphs our split-M kernel (exact fp32,
+        # the bias column sums ride along); below TALL_ROWS the cuBLAS call is one or two tiny launches either way.
+        tall = n >= TALL_ROWS
+        tn = kernels.gemm_tn if tall else (lambda a, b: torch.mm(a.t(), b))
         d_W3 = d_X = None
         if need[5] or need[7]:
             dXW = _aggregate(keepalive[1], bwd_view, dh, nflat, wflat if ctx.weighted else None)
             if need[7]:
-                d_W3 = torch.mm(X.t(), dXW)
+                d_W3 = tn(X, dXW)
             if need[5]:
                 d_X = torch.mm(dXW, W3.t())
-        d_lb = dP.sum(0) if need[12] else None
+        d_lb = None
+        d_Lc_zr = d_Lc_h = None
+        if tall and need[12] and need[10] and need[11]:          # the two GEMMs that read all of dP also sum its columns
+            d_Lc_zr, lb_zr = kernels.gemm_tn(H, dP[:, :2 * hid], colsum=True)
+            d_Lc_h, lb_h = kernels.gemm_tn(HR, dP[:, 2 * hid:], colsum=True)
+            d_lb = torch.cat((lb_zr, lb_h))
+        else:
+            d_lb = dP.sum(0) if need[12] else None
+            d_Lc_zr = tn(H, dP[:, :2 * hid]) if need[10] else None
+            d_Lc_h = tn(HR, dP[:, 2 * hid:]) if need[11] else None
         d_La = None
         if need[9]:
             d_La = torch.empty_like(La)
             for g in range(3):
-                torch.mm(h[:, g * hid:(g + 1) * hid].t(), dP[:, g * hid:(g + 1) * hid], out=d_La[g])
-        d_Lc_zr = torch.mm(H.t(), dP[:, :2 * hid]) if need[10] else None
-        d_Lc_h = torch.mm(HR.t(), dP[:, 2 * hid:]) if need[11] else None
+                blk = slice(g * hid, (g + 1) * hid)
+                if tall:
+                    kernels.gemm_tn(h[:, blk], dP[:, blk], out=d_La[g])
+                else:
+                    torch.mm(h[:, blk].t(), dP[:, blk], out=d_La[g])
         return (None, None, None, None, None, d_X, dH if need[6] else None, d_W3, d_b3, d_La, d_Lc_zr, d_Lc_h, d_lb)
 
 
