@@ -36,6 +36,24 @@ __global__ void __launch_bounds__(kGateThreads) bias_clamp_kernel(float* __restr
   }
 }
 
+// four elements per thread (cols % 4 == 0, 16-byte aligned): the bias index does not wrap inside a float4
+__global__ void __launch_bounds__(kGateThreads) bias_clamp4_kernel(float4* __restrict__ a, const float* __restrict__ bias,
+                                                                  int64_t n4, int cols, float lo, float hi) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = a[i];
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + static_cast<int>((i * 4) % cols)));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    v.x = (v.x != v.x) ? v.x : fminf(fmaxf(v.x, lo), hi);
+    v.y = (v.y != v.y) ? v.y : fminf(fmaxf(v.y, lo), hi);
+    v.z = (v.z != v.z) ? v.z : fminf(fmaxf(v.z, lo), hi);
+    v.w = (v.w != v.w) ? v.w : fminf(fmaxf(v.w, lo), hi);
+    a[i] = v;
+  }
+}
+
 // d_a = d_y where the clamped value lies strictly inside (lo, hi), else 0 (torch.clamp passes the gradient on the
 // closed interval of the UNCLAMPED value; the two differ only when the pre-clamp value equals a bound exactly)
 __global__ void __launch_bounds__(kGateThreads) clamp_bwd_kernel(const float* __restrict__ y, const float* __restrict__ d_y,
@@ -94,60 +112,119 @@ __global__ void __launch_bounds__(kGateThreads) update_bwd_kernel(const float* _
 // ---- the same gate arithmetic on the block layout of the one-Function cell (ops_tgcn.py): the three gate
 // pre-activations are the column blocks (z | r | h) of ONE [rows, 3*hid] matrix p, so that every GEMM that produces or
 // consumes them works on a column block in place and the bias / weight gradients are one reduction / one GEMM each.
+// V = 4: one float4 per thread and step (hid % 4 == 0, 16-byte aligned bases); V = 1: scalar.
+template <int V> struct GateVec;
+template <> struct GateVec<1> {
+  using T = float;
+  static __device__ __forceinline__ void get(const T& v, float (&a)[1]) { a[0] = v; }
+  static __device__ __forceinline__ T make(const float (&a)[1]) { return a[0]; }
+};
+template <> struct GateVec<4> {
+  using T = float4;
+  static __device__ __forceinline__ void get(const T& v, float (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+  static __device__ __forceinline__ T make(const float (&a)[4]) { return make_float4(a[0], a[1], a[2], a[3]); }
+};
+template <int V> __device__ __forceinline__ void ldg_v(const float* p, float (&a)[V]) {
+  GateVec<V>::get(*reinterpret_cast<const typename GateVec<V>::T*>(p), a);
+}
+template <int V> __device__ __forceinline__ void st_v(float* p, const float (&a)[V]) {
+  *reinterpret_cast<typename GateVec<V>::T*>(p) = GateVec<V>::make(a);
+}
+
+// i runs over the [rows, hid] elements in steps of V; q is the matching element of the z block of p / d_p
+#define STG_CELL_LOOP(V)                                                                                           \
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * V;                                          \
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; i < n; i += stride)
+
+template <int V>
 __global__ void __launch_bounds__(kGateThreads) cell_reset_fwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
                                                                      float* __restrict__ hr, int64_t n, int hid) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  STG_CELL_LOOP(V) {
     const int64_t r = i / hid;
-    const int j = static_cast<int>(i - r * hid);
-    hr[i] = h[i] * sigmoidf_(p[r * 3 * hid + hid + j]);
+    const int64_t q = r * 3 * hid + (i - r * hid);
+    float pr[V], hv[V], o[V];
+    ldg_v<V>(p + q + hid, pr);
+    ldg_v<V>(h + i, hv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = hv[k] * sigmoidf_(pr[k]);
+    st_v<V>(hr + i, o);
   }
 }
 
 // d_p[:, r block] = d_hr * h * r * (1 - r);  d_h += d_hr * r   (d_h already holds the update gate's share)
+template <int V>
 __global__ void __launch_bounds__(kGateThreads) cell_reset_bwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
                                                                      const float* __restrict__ d_hr, float* __restrict__ d_p,
                                                                      float* __restrict__ d_h, int64_t n, int hid) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  STG_CELL_LOOP(V) {
     const int64_t r = i / hid;
-    const int j = static_cast<int>(i - r * hid);
-    const int64_t q = r * 3 * hid + hid + j;
-    const float s = sigmoidf_(p[q]);
-    const float g = d_hr[i];
-    d_p[q] = g * h[i] * s * (1.f - s);
-    d_h[i] += g * s;
+    const int64_t q = r * 3 * hid + (i - r * hid) + hid;
+    float pr[V], hv[V], g[V], dh[V], dp[V];
+    ldg_v<V>(p + q, pr);
+    ldg_v<V>(h + i, hv);
+    ldg_v<V>(d_hr + i, g);
+    ldg_v<V>(d_h + i, dh);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float s = sigmoidf_(pr[k]);
+      dp[k] = g[k] * hv[k] * s * (1.f - s);
+      dh[k] += g[k] * s;
+    }
+    st_v<V>(d_p + q, dp);
+    st_v<V>(d_h + i, dh);
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kGateThreads) cell_update_fwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
                                                                       float* __restrict__ out, int64_t n, int hid) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  STG_CELL_LOOP(V) {
     const int64_t r = i / hid;
-    const int j = static_cast<int>(i - r * hid);
-    const int64_t q = r * 3 * hid + j;
-    const float z = sigmoidf_(p[q]);
-    out[i] = z * h[i] + (1.f - z) * tanhf(p[q + 2 * hid]);
+    const int64_t q = r * 3 * hid + (i - r * hid);
+    float pz[V], ph[V], hv[V], o[V];
+    ldg_v<V>(p + q, pz);
+    ldg_v<V>(p + q + 2 * hid, ph);
+    ldg_v<V>(h + i, hv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float z = sigmoidf_(pz[k]);
+      o[k] = z * hv[k] + (1.f - z) * tanhf(ph[k]);
+    }
+    st_v<V>(out + i, o);
   }
 }
 
 // d_p[:, z block], d_p[:, h block] and d_h = d_out * z (the reset gate's share is added by cell_reset_bwd_kernel)
+template <int V>
 __global__ void __launch_bounds__(kGateThreads) cell_update_bwd_kernel(const float* __restrict__ p, const float* __restrict__ h,
                                                                       const float* __restrict__ d_out, float* __restrict__ d_p,
                                                                       float* __restrict__ d_h, int64_t n, int hid) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  STG_CELL_LOOP(V) {
     const int64_t r = i / hid;
-    const int j = static_cast<int>(i - r * hid);
-    const int64_t q = r * 3 * hid + j;
-    const float z = sigmoidf_(p[q]);
-    const float t = tanhf(p[q + 2 * hid]);
-    const float g = d_out[i];
-    d_p[q] = g * (h[i] - t) * z * (1.f - z);
-    d_p[q + 2 * hid] = g * (1.f - z) * (1.f - t * t);
-    d_h[i] = g * z;
+    const int64_t q = r * 3 * hid + (i - r * hid);
+    float pz[V], ph[V], hv[V], g[V], dz[V], dc[V], dh[V];
+    ldg_v<V>(p + q, pz);
+    ldg_v<V>(p + q + 2 * hid, ph);
+    ldg_v<V>(h + i, hv);
+    ldg_v<V>(d_out + i, g);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float z = sigmoidf_(pz[k]);
+      const float t = tanhf(ph[k]);
+      dz[k] = g[k] * (hv[k] - t) * z * (1.f - z);
+      dc[k] = g[k] * (1.f - z) * (1.f - t * t);
+      dh[k] = g[k] * z;
+    }
+    st_v<V>(d_p + q, dz);
+    st_v<V>(d_p + q + 2 * hid, dc);
+    st_v<V>(d_h + i, dh);
   }
+}
+#undef STG_CELL_LOOP
+
+template <class... P>
+inline bool cell_vec_ok(int hid, P... ptrs) {
+  return hid % 4 == 0 && (aligned16(ptrs) && ...);
 }
 
 }  // namespace
@@ -160,7 +237,8 @@ STG_API int stg_tgcn_reset_fwd_f32(const float* p, const float* h, float* hr, in
   if (rows == 0) return STG_OK;
   STG_CHECK_ARG(p && h && hr, "NULL tensor");
   const int64_t n = rows * hid;
-  cell_reset_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, hr, n, hid);
+  if (cell_vec_ok(hid, p, h, hr)) cell_reset_fwd_kernel<4><<<gate_blocks(n / 4), kGateThreads, 0, as_stream(stream)>>>(p, h, hr, n, hid);
+  else cell_reset_fwd_kernel<1><<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, hr, n, hid);
   STG_LAUNCH_CHECK("cell_reset_fwd_kernel");
   return STG_OK;
 }
@@ -171,7 +249,9 @@ STG_API int stg_tgcn_reset_bwd_f32(const float* p, const float* h, const float* 
   if (rows == 0) return STG_OK;
   STG_CHECK_ARG(p && h && d_hr && d_p && d_h, "NULL tensor");
   const int64_t n = rows * hid;
-  cell_reset_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_hr, d_p, d_h, n, hid);
+  if (cell_vec_ok(hid, p, h, d_hr, d_p, d_h))
+    cell_reset_bwd_kernel<4><<<gate_blocks(n / 4), kGateThreads, 0, as_stream(stream)>>>(p, h, d_hr, d_p, d_h, n, hid);
+  else cell_reset_bwd_kernel<1><<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_hr, d_p, d_h, n, hid);
   STG_LAUNCH_CHECK("cell_reset_bwd_kernel");
   return STG_OK;
 }
@@ -181,7 +261,8 @@ STG_API int stg_tgcn_update_fwd_f32(const float* p, const float* h, float* out, 
   if (rows == 0) return STG_OK;
   STG_CHECK_ARG(p && h && out, "NULL tensor");
   const int64_t n = rows * hid;
-  cell_update_fwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, out, n, hid);
+  if (cell_vec_ok(hid, p, h, out)) cell_update_fwd_kernel<4><<<gate_blocks(n / 4), kGateThreads, 0, as_stream(stream)>>>(p, h, out, n, hid);
+  else cell_update_fwd_kernel<1><<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, out, n, hid);
   STG_LAUNCH_CHECK("cell_update_fwd_kernel");
   return STG_OK;
 }
@@ -192,7 +273,9 @@ STG_API int stg_tgcn_update_bwd_f32(const float* p, const float* h, const float*
   if (rows == 0) return STG_OK;
   STG_CHECK_ARG(p && h && d_out && d_p && d_h, "NULL tensor");
   const int64_t n = rows * hid;
-  cell_update_bwd_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_out, d_p, d_h, n, hid);
+  if (cell_vec_ok(hid, p, h, d_out, d_p, d_h))
+    cell_update_bwd_kernel<4><<<gate_blocks(n / 4), kGateThreads, 0, as_stream(stream)>>>(p, h, d_out, d_p, d_h, n, hid);
+  else cell_update_bwd_kernel<1><<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(p, h, d_out, d_p, d_h, n, hid);
   STG_LAUNCH_CHECK("cell_update_bwd_kernel");
   return STG_OK;
 }
@@ -203,7 +286,10 @@ STG_API int stg_bias_clamp_f32(float* a, const float* bias, int64_t rows, int32_
   if (rows == 0) return STG_OK;
   STG_CHECK_ARG(a != nullptr, "a is NULL");
   const int64_t n = rows * cols;
-  bias_clamp_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(a, bias, n, cols, lo, hi);
+  if (cols % 4 == 0 && aligned16(a) && (bias == nullptr || aligned16(bias)))
+    bias_clamp4_kernel<<<gate_blocks(n / 4), kGateThreads, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(a), bias, n / 4, cols,
+                                                                                 lo, hi);
+  else bias_clamp_kernel<<<gate_blocks(n), kGateThreads, 0, as_stream(stream)>>>(a, bias, n, cols, lo, hi);
   STG_LAUNCH_CHECK("bias_clamp_kernel");
   return STG_OK;
 }
