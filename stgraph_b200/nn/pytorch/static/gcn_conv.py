@@ -5,8 +5,9 @@ interchange with the reference layer:
 
     h' = act( norm * sum_{u in in(v)} (h W)[u] * norm[u] [* w_e] + b )
 
-``torch.mm`` stays a library GEMM (it is not the hot path); the aggregation is the traced
-vertex program, lowered to the fused sm_100a gather kernel (``csrc/agg.cu``).
+``X . W`` stays a library GEMM (it is not the hot path; only its weight gradient, a reduction over all
+vertices, runs in our split-M kernel on large graphs: ``ops_gcn.dense_transform``); the aggregation is the
+traced vertex program, lowered to the fused sm_100a gather kernel (``csrc/agg.cu``).
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ from torch import Tensor, nn
 
 from ....compiler import STGraph
 from ....compiler.backend.pytorch.torch_callback import STGraphBackendTorch
+from ....ops_gcn import dense_transform
 from ....utils.constants import SizeConstants
 
 
@@ -50,7 +52,7 @@ class GCNConv(nn.Module):
         if (len(norm.shape) != SizeConstants.NODE_NORM_SIZE.value or norm.shape[1] != 1
                 or norm.shape[0] != graph.num_local_nodes()):
             raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_local_nodes, 1)")
-        h = torch.mm(h, self.weight)
+        h = dense_transform(h, self.weight)
         h = partitioned_gcn_aggregate(graph, h, norm)
         if self.bias is not None:
             h = h + self.bias
@@ -68,7 +70,7 @@ class GCNConv(nn.Module):
                 or norm.shape[0] != graph.get_num_nodes()):
             raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_nodes, 1)")
 
-        h = torch.mm(h, self.weight)
+        h = dense_transform(h, self.weight)
 
         if edge_weight is None:
 

@@ -49,3 +49,34 @@ def gcn_aggregate(graph, h, norm, edge_weight=None):
     fwd = graph.fwd_view()
     keep = (graph._forward_graph, graph._backward_graph)
     return _GcnAggregate.apply(fwd, bwd, keep, h, norm, edge_weight)
+
+
+#: rows from which the weight gradient of :func:`dense_transform` goes through ``kernels.gemm_tn`` instead of cuBLAS
+TALL_ROWS = 32768
+
+
+class _DenseTransform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, weight):
+        ctx.save_for_backward(h, weight)
+        return torch.mm(h, weight)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, weight = ctx.saved_tensors
+        d_h = torch.mm(g, weight.t()) if ctx.needs_input_grad[0] else None
+        d_w = None
+        if ctx.needs_input_grad[1]:
+            hh = h if h.stride(-1) == 1 else h.contiguous()
+            gg = g if g.stride(-1) == 1 else g.contiguous()
+            d_w = kernels.gemm_tn(hh, gg)
+        return d_h, d_w
+
+
+def dense_transform(h, weight):
+    """``h @ weight`` (GCNConv's ``X . W``, ``gcn_conv.py:160``): a library GEMM forward and for the input gradient; on
+    graphs of ``TALL_ROWS`` vertices and more the weight gradient ``h^T @ g`` -- a ``[K, N] x [N, Nc]`` product that
+    cuBLAS runs at a fraction of the machine -- goes through ``stg_gemm_tn_f32`` (exact fp32, deterministic)."""
+    if h.is_cuda and h.dtype == torch.float32 and weight.dtype == torch.float32 and h.dim() == 2 and h.shape[0] >= TALL_ROWS:
+        return _DenseTransform.apply(h, weight)
+    return torch.mm(h, weight)

@@ -102,3 +102,33 @@ def test_tgcn_cell_large_graph_uses_gemm_tn_and_matches_pieces(cuda):
     for k in res[0][1]:
         ga, gb = res[0][1][k], res[1][1][k]
         assert (ga - gb).abs().max() <= 5e-5 * ga.abs().max() + 1e-8, (k, float((ga - gb).abs().max()), float(ga.abs().max()))
+
+
+def test_gcnconv_weight_gradient_through_gemm_tn(cuda):
+    """GCNConv on a graph above ops_gcn.TALL_ROWS vertices: the weight gradient (gemm_tn) equals the cuBLAS one."""
+    from stgraph_b200 import ops_gcn
+    from stgraph_b200.graph import StaticGraph
+    from stgraph_b200.nn.pytorch import GCNConv
+
+    n, e = ops_gcn.TALL_ROWS + 777, 300000
+    g = torch.Generator(device=cuda).manual_seed(11)
+    src = torch.randint(0, n, (e,), device=cuda, generator=g)
+    dst = torch.randint(0, n, (e,), device=cuda, generator=g)
+    graph = StaticGraph(torch.stack([src, dst], 1), None, n)
+    graph.set_ndata("norm", graph.degree_norm())
+    torch.manual_seed(4)
+    layer = GCNConv(24, 10).to(cuda)
+    x = torch.randn(n, 24, device=cuda, generator=g, requires_grad=True)
+    gout = torch.randn(n, 10, device=cuda, generator=g)
+    layer(graph, x).backward(gout)
+    got_w, got_x = layer.weight.grad.clone(), x.grad.clone()
+    layer.zero_grad()
+    x.grad = None
+    old = ops_gcn.TALL_ROWS
+    ops_gcn.TALL_ROWS = 1 << 62          # cuBLAS path
+    try:
+        layer(graph, x).backward(gout)
+    finally:
+        ops_gcn.TALL_ROWS = old
+    assert (got_w - layer.weight.grad).abs().max() <= 2e-5 * layer.weight.grad.abs().max()
+    torch.testing.assert_close(got_x, x.grad, rtol=1e-6, atol=1e-6)
