@@ -160,11 +160,24 @@ class Context:
         return Executor(graph, forward_units, backward_units, grad_in, grad_out, out_vars)
 
 
+def _rebuild_stgraph(backend_cls):
+    return STGraph(backend_cls())
+
+
 class STGraph:
     def __init__(self, backend_framework: STGraphBackend):
         self._ctx_map = {}
         self._backend_framework = backend_framework
         self._run_cb = backend_framework.backend_cb
+
+    # Traced programs and executors are caches of THIS instance, and the backend object holds the ``torch`` module: a
+    # deep copy / pickle of the layer that owns an STGraph (``copy.deepcopy(model)``, ``torch.save(model)``) gets a fresh,
+    # empty one.  (The reference's layers cannot be copied or pickled at all for that reason.)
+    def __deepcopy__(self, memo):
+        return _rebuild_stgraph(type(self._backend_framework))
+
+    def __reduce__(self):
+        return _rebuild_stgraph, (type(self._backend_framework),)
 
     def compile(self, gnn_module, hetero_graph=False):
         namespace = [gnn_module, self._backend_framework.backend_module]

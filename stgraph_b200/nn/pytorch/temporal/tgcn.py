@@ -36,6 +36,12 @@ class TGCN(torch.nn.Module):
         self.conv_h = GCNConv(self.in_channels, self.out_channels, activation=None)
         self.linear_h = torch.nn.Linear(2 * self.out_channels, self.out_channels)
 
+    def __getstate__(self):
+        # the parameter pack of the fused cell holds non-leaf tensors: never part of a copy / pickle of the module
+        state = self.__dict__.copy()
+        state.pop("_pack_cache", None)
+        return state
+
     def _set_hidden_state(self, X, H):
         if H is None:
             H = torch.zeros(X.shape[0], self.out_channels).to(X.device)
@@ -68,6 +74,10 @@ class TGCN(torch.nn.Module):
     def _check_fused_inputs(self, g, edge_weight):
         from ....utils.constants import SizeConstants
 
+        for conv in (self.conv_z, self.conv_r, self.conv_h):
+            if conv.bias is None or conv.activation is not None:
+                raise RuntimeError("the fused TGCN cell needs the three convolutions as the reference builds them "
+                                   "(bias, no activation); use TGCN(fused=False)")
         norm = g.get_ndata("norm")
         if norm is None:
             raise KeyError("StaticGraph passed to GCNConv forward pass does not contain 'norm' node data")
