@@ -823,6 +823,14 @@ int launch_agg(const AggParams& p, cudaStream_t stream) {
   return STG_OK;
 }
 
+inline bool narrow_vec2() {
+  static const bool v = [] {
+    const char* e = getenv("STG_AGG_NARROW_VEC2");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return v;
+}
+
 template <int VEC, int MODE>
 int dispatch_group(const AggParams& p, cudaStream_t stream, int avg_degree) {
   const int nvec = p.width / VEC;
@@ -897,6 +905,11 @@ int agg_scaled_sum_device(const StgCsrView* g, const float* x, int32_t feat, con
   int vec = 1;
   if (feat % 4 == 0 && p.ld % 4 == 0 && p.ld_out % 4 == 0 && al16) vec = 4;
   else if (feat % 2 == 0 && p.ld % 2 == 0 && p.ld_out % 2 == 0 && al8) vec = 2;
+  // 33..64 floats per row with 128-bit loads are two rows per warp on the static schedule; 64-bit loads make them one
+  // row per warp, which runs on the global row queue (STG_AGG_NARROW_VEC2=0 keeps the 128-bit form)
+  if (vec == 4 && feat > 32 && feat <= 64 && nparts == 0 && narrow_vec2() && g->work_queue != nullptr &&
+      g->num_nodes >= 2 * sm_count() * 4 * (kBlockThreads / 32))
+    vec = 2;
   const int chunk = 32 * 4 * vec;  // widest tile one launch covers
   for (int f0 = 0; f0 < feat; f0 += chunk) {
     p.x = x ? x + f0 : nullptr;
