@@ -386,18 +386,43 @@ def reference_kernels():
             out_ms[k["name"] + "_" + k["direction"]] = a.elapsed_time(b) / reps
         return out_ms
 
+    def ours_gcn(graph, feat, n):
+        """Device time of OUR aggregation kernels (torch.profiler kernel durations, no host time) for the same unit:
+        forward on the in-edge CSR + backward on the out-edge CSR, width `feat`."""
+        from torch.profiler import ProfilerActivity, profile
+
+        norm = graph.degree_norm().reshape(-1).contiguous()
+        x = torch.rand(n, feat, device=dev)
+        outs = [torch.empty_like(x), torch.empty_like(x)]
+
+        def run():
+            kernels.agg_scaled_sum_graph(graph._forward_graph, x, norm, None, norm, out=outs[0])
+            kernels.agg_scaled_sum_graph(graph._backward_graph, x, norm, None, norm, out=outs[1])
+
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(20):
+                run()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        return sum(e.device_time for e in evs) / 1e3 / 20
+
     d = synthetic.cora_shaped(seed=0, device=dev)
     g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
     t = time_case("gcn_f16", g, 16, d["num_nodes"], int(d["src"].shape[0]))
     if t:
         res["config1_gcn_f16_kernels_ms"] = t
         res["config1_epoch_kernels_ms_estimate"] = 2 * sum(t.values())        # two layers (the F=7 layer timed as F=16)
+        res["config1_gcn_f16_our_kernels_ms"] = ours_gcn(g, 16, d["num_nodes"])   # fwd + bwd launch of ours, same unit
     d = synthetic.wikimaths_shaped(seed=0, device=dev)
     g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
     t = time_case("gcn_f16", g, 16, d["num_nodes"], int(d["src"].shape[0]))
     if t:
         res["config2_gcn_f16_kernels_ms"] = t
         res["config2_epoch_kernels_ms_estimate"] = 3 * 723 * sum(t.values())  # three convolutions per timestep, fwd + bwd
+        res["config2_gcn_f16_our_kernels_ms"] = ours_gcn(g, 16, d["num_nodes"])
     d = synthetic.arxiv_shaped(seed=0, device=dev)
     g = StaticGraph(torch.stack([d["src"], d["dst"]], 1), None, d["num_nodes"])
     t = time_case("gat_h8d16", g, 128, d["num_nodes"], int(d["src"].shape[0]), reps=5)
