@@ -56,3 +56,23 @@ def test_argument_validation_without_gpu():
     v.row_offset = 1  # never dereferenced: feat is rejected first
     rc = lib.stg_agg_scaled_sum_f32(ctypes.byref(v), None, 0, None, None, None, None, None)
     assert rc == -1 and b"feat" in lib.stg_last_error()
+
+
+def test_gemm_tn_workspace_query_and_argument_checks_without_gpu():
+    """stg_gemm_tn_workspace_bytes is a host-side query: slabs x (K*Nc + Nc) floats, none for small M; the entry point
+    rejects bad shapes / a missing workspace before any launch."""
+    lib = _lib.load()
+    for m, k, nc in ((1_000_000, 64, 64), (2_449_029, 100, 47), (1_000_000, 32, 192), (50_000, 8, 48)):
+        b = lib.stg_gemm_tn_workspace_bytes(m, k, nc)
+        per_slab = (k * nc + nc) * 4
+        assert b > 0 and b % per_slab == 0
+        slabs = b // per_slab
+        assert 2 <= slabs <= 2 * 148 and m // slabs >= 128          # about two CTAs per SM, at least 128 rows per slab
+    assert lib.stg_gemm_tn_workspace_bytes(100, 64, 64) == 0           # one slab: the result is written directly
+    assert lib.stg_gemm_tn_workspace_bytes(0, 64, 64) == 0
+    assert lib.stg_gemm_tn_f32(None, 64, None, 64, 10, 0, 64, None, None, None, 0, None) == -1
+    assert b"shape" in lib.stg_last_error()
+    assert lib.stg_gemm_tn_f32(1, 8, 1, 64, 10, 64, 64, 1, None, None, 0, None) == -1       # lda < K
+    assert b"leading" in lib.stg_last_error()
+    assert lib.stg_gemm_tn_f32(1, 64, 1, 64, 1_000_000, 64, 64, 1, None, None, 0, None) == -1   # workspace missing
+    assert b"workspace" in lib.stg_last_error()
