@@ -41,7 +41,8 @@ WAIT_TIMEOUT_CYCLES = int(os.environ.get("STG_PEER_WAIT_CYCLES", str(4 << 30)))
 
 class HaloExchange:
     def __init__(self, plan, feat: int, ns_own: torch.Tensor | None, ns_halo: torch.Tensor | None,
-                 mode: str | None = None, gather_blocks: int = 0, push_blocks: int = 64):
+                 mode: str | None = None, gather_blocks: int = 0, push_blocks: int = 64,
+                 edge_scale: torch.Tensor | None = None):
         import torch.distributed._symmetric_memory as symm_mem
 
         from .. import kernels
@@ -102,8 +103,10 @@ class HaloExchange:
         # the two sub-CSRs of my rows with their packed {col, scale} metadata (scales are fixed per graph: norm)
         self.v_own, _ = plan.split_views()
         self.v_halo = plan.halo_compact_view()
-        self.meta_own = kernels.pack_edge_meta(self.v_own, ns_own, None, device=dev) if plan.own_cols.numel() else None
-        self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, None, device=dev)
+        # edge_scale (edge weights): one value per GLOBAL edge id, replicated on every rank like the structure; the
+        # sub-CSRs carry the global ids of their edges, so the product ns * es is folded into the packed metadata
+        self.meta_own = kernels.pack_edge_meta(self.v_own, ns_own, edge_scale, device=dev) if plan.own_cols.numel() else None
+        self.meta_halo = (kernels.pack_edge_meta(self.v_halo, ns_halo, edge_scale, device=dev)
                           if plan.halo_cols.numel() else None)
         self.ns_own, self.ns_halo = ns_own, ns_halo
         self.profile = None            # set to [] to collect per-call CUDA events (bench.py `segments`)

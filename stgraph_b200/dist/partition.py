@@ -157,24 +157,35 @@ class PartitionedGraph:
             self._halo_scalars[key] = (plan.halo_vector(own_values.reshape(-1).contiguous()), own_values)
         return self._halo_scalars[key][0]
 
-    def exchange(self, direction: str, feat: int, nbr_scale: torch.Tensor | None):
-        """The :class:`HaloExchange` of (direction, width, source scale); collective on first use."""
+    def exchange(self, direction: str, feat: int, nbr_scale: torch.Tensor | None, edge_scale: torch.Tensor | None = None):
+        """The :class:`HaloExchange` of (direction, width, source scale, edge scale); collective on first use."""
         from .exchange import HaloExchange
 
-        key = (direction, int(feat), None if nbr_scale is None else (nbr_scale.data_ptr(), nbr_scale._version))
+        def ident(t):
+            return None if t is None else (t.data_ptr(), t._version)
+
+        key = (direction, int(feat), ident(nbr_scale), ident(edge_scale))
         ex = self._exchanges.get(key)
         if ex is None:
             plan = self.halo_plans()[0 if direction == "fwd" else 1]
             ns_own = None if nbr_scale is None else nbr_scale.reshape(-1).contiguous()
             ns_halo = None if nbr_scale is None else self.halo_scalars(direction, ns_own)
-            ex = HaloExchange(plan, feat, ns_own, ns_halo)
-            ex._scale_ref = nbr_scale
+            es = None
+            if edge_scale is not None:
+                es = edge_scale.reshape(-1).contiguous()
+                if es.numel() != self.graph.get_num_edges():
+                    raise ValueError(f"edge_scale must hold one value per edge of the WHOLE graph ({self.graph.get_num_edges()}), "
+                                     f"got {es.numel()}")
+            ex = HaloExchange(plan, feat, ns_own, ns_halo, edge_scale=es)
+            ex._scale_ref = (nbr_scale, edge_scale)
             self._exchanges[key] = ex
         return ex
 
-    def aggregate(self, direction: str, x_own: torch.Tensor, nbr_scale=None, row_scale=None, out=None) -> torch.Tensor:
-        """``out[v] = row_scale[v] * sum_{u in nbrs(v)} nbr_scale[u] * x[u]`` for my vertices ``v``; every tensor holds
-        local rows only (``[n_own, ...]``), remote source rows travel as halo (see ``dist/exchange.py``)."""
+    def aggregate(self, direction: str, x_own: torch.Tensor, nbr_scale=None, row_scale=None, out=None,
+                  edge_scale=None) -> torch.Tensor:
+        """``out[v] = row_scale[v] * sum_{u in nbrs(v)} nbr_scale[u] * edge_scale[eid(u, v)] * x[u]`` for my vertices ``v``;
+        the vertex tensors hold local rows only (``[n_own, ...]``), ``edge_scale`` holds the WHOLE graph's edge values in
+        edge-id order (replicated, like the structure); remote source rows travel as halo (see ``dist/exchange.py``)."""
         if x_own.shape[0] != self.n_own:
             raise ValueError(f"x_own must hold the {self.n_own} local rows, got {x_own.shape[0]}")
         x_own = x_own.contiguous()
@@ -182,7 +193,7 @@ class PartitionedGraph:
         if out is None:
             out = torch.empty_like(x_own)
         rs = None if row_scale is None else row_scale.reshape(-1).contiguous()
-        return self.exchange(direction, feat, nbr_scale).aggregate(x_own.reshape(self.n_own, feat), rs, out)
+        return self.exchange(direction, feat, nbr_scale, edge_scale).aggregate(x_own.reshape(self.n_own, feat), rs, out)
 
     def local_rows(self, direction: str):
         return self.own_lo, self.own_hi
@@ -193,17 +204,20 @@ class _PartitionedGcnAggregate(torch.autograd.Function):
     (a gather both ways, like the reference's K0/K1 pair, ``gcn_conv.py:162-166``)."""
 
     @staticmethod
-    def forward(ctx, pg, h, norm):
-        ctx.pg, ctx.norm = pg, norm
-        return pg.aggregate("fwd", h, norm, norm)
+    def forward(ctx, pg, h, norm, edge_weight):
+        ctx.pg, ctx.norm, ctx.edge_weight = pg, norm, edge_weight
+        return pg.aggregate("fwd", h, norm, norm, edge_scale=edge_weight)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return None, ctx.pg.aggregate("bwd", grad_out.contiguous(), ctx.norm, ctx.norm), None
+        # the out-edge CSR carries the forward edge ids: the same weights apply (no gradient for them, like the reference)
+        return None, ctx.pg.aggregate("bwd", grad_out.contiguous(), ctx.norm, ctx.norm, edge_scale=ctx.edge_weight), None, None
 
 
-def partitioned_gcn_aggregate(pg: PartitionedGraph, h: torch.Tensor, norm: torch.Tensor) -> torch.Tensor:
-    return _PartitionedGcnAggregate.apply(pg, h, norm)
+def partitioned_gcn_aggregate(pg: PartitionedGraph, h: torch.Tensor, norm: torch.Tensor, edge_weight=None) -> torch.Tensor:
+    if edge_weight is not None and edge_weight.requires_grad:
+        raise RuntimeError("edge_weight gets no gradient on a PartitionedGraph (nor in the reference's GCNConv)")
+    return _PartitionedGcnAggregate.apply(pg, h, norm, edge_weight)
 
 
 def all_reduce_gradients(module_or_params, group=None):

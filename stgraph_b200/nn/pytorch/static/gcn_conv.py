@@ -44,8 +44,6 @@ class GCNConv(nn.Module):
         """``graph`` is a :class:`stgraph_b200.dist.PartitionedGraph`: ``h`` and the result hold this rank's rows."""
         from ....dist.partition import partitioned_gcn_aggregate
 
-        if edge_weight is not None:
-            raise NotImplementedError("edge_weight is not supported on a PartitionedGraph")
         norm = graph.get_ndata("norm")
         if norm is None:
             raise KeyError("PartitionedGraph passed to GCNConv forward pass does not contain 'norm' node data")
@@ -53,7 +51,7 @@ class GCNConv(nn.Module):
                 or norm.shape[0] != graph.num_local_nodes()):
             raise ValueError("Node data 'norm' passed to GCNConv should be of shape (num_local_nodes, 1)")
         h = dense_transform(h, self.weight)
-        h = partitioned_gcn_aggregate(graph, h, norm)
+        h = partitioned_gcn_aggregate(graph, h, norm, edge_weight)      # edge_weight: [E, 1] of the WHOLE graph, edge-id order
         if self.bias is not None:
             h = h + self.bias
         if self.activation:

@@ -60,6 +60,32 @@ def main():
                 if rep == 0:
                     d1 = (got - single[lo:hi]).abs()
                     assert bool((d1.cpu().double() <= 2e-6 * mag.double() + 1e-30).all()), ("vs single GPU", feat, direction)
+    # ---- edge weights: one value per global edge id, replicated; aggregation and layer against the single-GPU path
+    w = torch.rand(e, 1, device=dev, generator=torch.Generator(device=dev).manual_seed(21)) + 0.25
+    dist.broadcast(w, 0)
+    x = torch.randn(n, 48, device=dev, generator=torch.Generator(device=dev).manual_seed(22))
+    for direction, view in (("fwd", g.fwd_view()), ("bwd", g.bwd_view())):
+        single = kernels.agg_scaled_sum(view, x, norm.reshape(-1), w.reshape(-1), norm.reshape(-1))
+        mag = kernels.agg_scaled_sum(view, x.abs(), norm.reshape(-1), w.reshape(-1), norm.reshape(-1))
+        got = pg.aggregate(direction, x[lo:hi].contiguous(), nl, nl, edge_scale=w)
+        assert bool(((got - single[lo:hi]).abs() <= 2e-6 * mag[lo:hi] + 1e-30).all()), ("edge weights", direction)
+    torch.manual_seed(4)
+    lw = GCNConv(48, 12).to(dev)
+    for p in lw.parameters():
+        dist.broadcast(p.data, 0)
+    gw = torch.randn(n, 12, device=dev, generator=torch.Generator(device=dev).manual_seed(23))
+    xf = x.clone().requires_grad_(True)
+    full = lw(g, xf, edge_weight=w)
+    full.backward(gw)
+    ref_w, ref_x = lw.weight.grad.clone(), xf.grad.clone()
+    lw.zero_grad()
+    xl = x[lo:hi].clone().requires_grad_(True)
+    part = lw(pg, xl, edge_weight=w)
+    part.backward(gw[lo:hi])
+    all_reduce_gradients(lw)
+    assert float((part - full[lo:hi]).detach().abs().max()) <= 2e-5 * float(full.detach().abs().max()), "weighted partitioned GCN forward differs"
+    assert float((xl.grad - ref_x[lo:hi]).abs().max()) <= 2e-5 * float(ref_x.abs().max()) + 1e-7, "weighted dX differs"
+    assert float((lw.weight.grad - ref_w).abs().max()) <= 5e-4 * float(ref_w.abs().max()) + 1e-6, "weighted dW differs"
     # ---- the layer API: 2-layer GCN on the partitioned graph == the same model on the whole graph
     torch.manual_seed(3)
     l1, l2 = GCNConv(64, 32, activation=torch.relu).to(dev), GCNConv(32, 7).to(dev)
