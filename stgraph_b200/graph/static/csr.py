@@ -126,6 +126,8 @@ class CSR:
         tensors alive, so an address cannot be recycled under it; an in-place update through torch bumps the
         version and repacks.  Returns None (-> plain kernel) when there is nothing to pack, when packing is
         disabled, or on a miss during CUDA-graph capture (the cache must not own capture-pool memory).
+        A write that torch does not see -- ``t.data = ...`` / ``t.data.copy_()`` on some builds, a raw-pointer kernel --
+        does not move the version counter: call :meth:`invalidate_packed_meta` after it.
         """
         if not PACK_META or (nbr_scale is None and edge_scale is None) or self.num_edges == 0:
             return None
@@ -145,6 +147,14 @@ class CSR:
         meta = kernels.pack_edge_meta(self.view(), nbr_scale, edge_scale, device=self.row_offset.device)
         self._meta_cache = [(key, (nbr_scale, edge_scale), meta)] + self._meta_cache[:1]   # at most two live entries
         return meta
+
+    def invalidate_packed_meta(self):
+        """Drop the packed ``{col, scale}`` arrays (and re-enable packing): the next aggregation packs again from the
+        current contents of its scale tensors."""
+        if self._meta_misses > MAX_META_REPACKS:      # packing had been switched off by scales that changed every call
+            self.pack_enabled = bool(PACK_META)
+        self._meta_cache = []
+        self._meta_misses = 0
 
     # -- C-ABI view ------------------------------------------------------------
     def prepare_hub_schedule(self, sync: bool = True):

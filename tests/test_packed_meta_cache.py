@@ -72,3 +72,14 @@ def test_scales_that_change_every_call_stop_packing(csr):
         assert csr.packed_meta(torch.rand(3), None) is not None
     assert csr.packed_meta(torch.rand(3), None) is None
     assert csr.pack_enabled is False and csr._meta_cache == []
+
+
+def test_invalidate_after_a_write_torch_does_not_see(csr):
+    """A raw write (storage changed without a version bump) needs an explicit invalidate: the key is (address, version)."""
+    norm = torch.rand(3)
+    a = csr.packed_meta(norm, None)
+    norm.untyped_storage().copy_(torch.rand(3).untyped_storage())      # same address, same version counter
+    assert csr.packed_meta(norm, None) is a and len(csr.packs) == 1    # the documented caveat
+    csr.invalidate_packed_meta()
+    b = csr.packed_meta(norm, None)
+    assert b is not a and len(csr.packs) == 2 and csr.pack_enabled
