@@ -102,8 +102,9 @@ class TGCN(torch.nn.Module):
             return cache[1]
         packed = pack_parameters(*mods)
         stale = [False]
-        if packed[0].requires_grad:
-            packed[0].register_hook(lambda grad, flag=stale: flag.__setitem__(0, True))
+        for t in packed:          # any gradient that reaches the pack means a backward pass has run through it
+            if t.requires_grad:
+                t.register_hook(lambda grad, flag=stale: flag.__setitem__(0, True))
         self.__dict__["_pack_cache"] = (key, packed, stale)
         return packed
 

@@ -88,3 +88,17 @@ def test_layers_can_be_deep_copied_and_pickled():
         back = torch.load(buf, weights_only=False)
         for (k, p), (_, q), (_, r) in zip(layer.state_dict().items(), twin.state_dict().items(), back.state_dict().items()):
             assert torch.equal(p, q) and torch.equal(p, r), k
+
+
+def test_parameter_pack_goes_stale_with_partly_frozen_parameters():
+    """Frozen convolutions: the packed W3 / b3 get no gradient, the hook on the linear halves still marks the pack stale."""
+    torch.manual_seed(3)
+    cell = TGCN(3, 4)
+    for c in (cell.conv_z, cell.conv_r, cell.conv_h):
+        c.weight.requires_grad_(False)
+        c.bias.requires_grad_(False)
+    a = cell._packed_parameters()
+    assert not a[0].requires_grad and a[2].requires_grad
+    (a[2].sum() + a[5].sum()).backward()
+    assert cell._packed_parameters()[2] is not a[2]
+    assert cell.linear_z.weight.grad is not None and cell.conv_z.weight.grad is None
