@@ -141,7 +141,7 @@ class TGCN(torch.nn.Module):
         norm = g.get_ndata("norm") if hasattr(g, "get_ndata") else None
         return (all(type(c) is GCNConv and c.activation is None and c.bias is not None for c in convs)
                 and not hasattr(g, "num_local_nodes") and norm is not None and not norm.requires_grad
-                and not torch.is_autocast_enabled()          # the one-op cell computes in float32 only
+                and not torch.is_autocast_enabled("cuda")          # the one-op cell computes in float32 only
                 and (edge_weight is None or not edge_weight.requires_grad))
 
     def forward(self, g, X, edge_weight=None, H=None):

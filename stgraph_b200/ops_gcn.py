@@ -78,6 +78,6 @@ def dense_transform(h, weight):
     graphs of ``TALL_ROWS`` vertices and more the weight gradient ``h^T @ g`` -- a ``[K, N] x [N, Nc]`` product that
     cuBLAS runs at a fraction of the machine -- goes through ``stg_gemm_tn_f32`` (exact fp32, deterministic)."""
     if (h.is_cuda and h.dtype == torch.float32 and weight.dtype == torch.float32 and h.dim() == 2 and h.shape[0] >= TALL_ROWS
-            and not torch.is_autocast_enabled()):          # under autocast the GEMM runs in the autocast dtype: torch's own path
+            and not torch.is_autocast_enabled("cuda")):          # under autocast the GEMM runs in the autocast dtype: torch's own path
         return _DenseTransform.apply(h, weight)
     return torch.mm(h, weight)
